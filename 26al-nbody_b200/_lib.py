@@ -1,0 +1,154 @@
+"""ctypes binding of libal26b200.so (C-ABI: include/al26_b200.h).
+
+There is NO CPU fallback: if the shared library has not been built, or no sm_100 device is
+usable, the calls fail loudly.  Build with `python 26al-nbody_b200/csrc/build.py` (or
+`__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libal26b200.so")
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "al26_b200.h"))
+
+_D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_I32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_U8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_PD = C.POINTER(C.c_double)
+_PI64 = C.POINTER(C.c_int64)
+_PINT = C.POINTER(C.c_int)
+_VP = C.c_void_p
+
+ERROR_NAMES = {0: "AL26_OK", -1: "AL26_EINVAL", -2: "AL26_ESTATE", -3: "AL26_ETIME", -4: "AL26_ECAP",
+               -5: "AL26_ECUDA", -6: "AL26_ENCCL", -7: "AL26_ENODEV"}
+
+
+class Al26Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+# name -> (restype, argtypes).  Optional (nullable) array arguments are declared c_void_p.
+SIGNATURES = {
+    "al26_create": (_VP, [C.c_int]),
+    "al26_destroy": (None, [_VP]),
+    "al26_last_error": (C.c_char_p, [_VP]),
+    "al26_version": (C.c_int, []),
+    "al26_device_info": (C.c_int, [_VP, _PINT, _PINT, _PI64, _PI64]),
+    "al26_dist_unique_id": (C.c_int, [_VP]),
+    "al26_dist_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "al26_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
+    "al26_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
+    "al26_grav_set_time": (C.c_int, [_VP, C.c_double]),
+    "al26_grav_get_time": (C.c_int, [_VP, _PD]),
+    "al26_grav_evolve": (C.c_int, [_VP, C.c_double, _PI64, _PI64]),
+    "al26_grav_get_state": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
+    "al26_grav_energies": (C.c_int, [_VP, _PD, _PD, _PD]),
+    "al26_grav_initialize": (C.c_int, [_VP]),
+    "al26_grav_get_acc_jerk": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
+    "al26_grav_get_timesteps": (C.c_int, [_VP, C.c_int64, _D, _D]),
+    "al26_grav_set_timesteps": (C.c_int, [_VP, C.c_int64, _D, _D]),
+    "al26_grav_get_active": (C.c_int, [_VP, C.c_int64, _I32, _PI64, _PD]),
+    "al26_grav_get_last_active": (C.c_int, [_VP, C.c_int64, _I32, _PI64]),
+    "al26_grav_dbg_begin": (C.c_int, [_VP, C.c_double]),
+    "al26_grav_dbg_advance": (C.c_int, [_VP, C.c_int64, _PI64, _PINT]),
+    "al26_grav_dbg_finish": (C.c_int, [_VP]),
+    "al26_grav_force": (C.c_int, [_VP, C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32] + [_D] * 7),
+    "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
+    "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
+    "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
+    "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
+    "al26_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
+    "al26_enrich_step": (C.c_int, [_VP, C.c_int64, _D, _D, _VP] + [C.c_double] * 6 + [C.c_int, _I32, C.c_int64, _PI64]),
+    "al26_enrich_get": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed for this) and declare every prototype."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} not built: run `python 26al-nbody_b200/csrc/build.py`. "
+                "There is no CPU fallback for the B200 hot path.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(ctx, rc):
+    if rc != 0:
+        msg = load().al26_last_error(ctx)
+        raise Al26Error(rc, msg.decode() if msg else "")
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    """void* of an optional numpy array (None -> NULL)."""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Owns one al26_ctx (= one GPU).  Thin, unit-free wrapper used by gravity.py / enrichment.py."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = self.L.al26_create(int(device))
+        if not h:
+            msg = self.L.al26_last_error(None)
+            raise Al26Error(-7, (msg.decode() if msg else "al26_create failed") +
+                            " -- the B200 path has no CPU fallback")
+        self.h = C.c_void_p(h)
+        self.device = int(device)
+        self.rank, self.world = 0, 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.al26_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def chk(self, rc):
+        check(self.h, rc)
+
+    def device_info(self):
+        sm, khz, fr, tot = C.c_int(0), C.c_int(0), C.c_int64(0), C.c_int64(0)
+        self.chk(self.L.al26_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(fr), C.byref(tot)))
+        return {"sm_count": sm.value, "clock_khz": khz.value, "free_bytes": fr.value, "total_bytes": tot.value}
+
+    def dist_init(self, rank, world, unique_id_bytes):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
+        self.chk(self.L.al26_dist_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p) if buf else None))
+        self.rank, self.world = int(rank), int(world)
+
+    def last_device_ms(self):
+        ms, nl = C.c_double(0), C.c_int64(0)
+        self.chk(self.L.al26_last_device_ms(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+
+def dist_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = load().al26_dist_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise Al26Error(rc, load().al26_last_error(None).decode())
+    return buf.raw

@@ -1,0 +1,1066 @@
+// api.cu -- the C-ABI of libal26b200.so (include/al26_b200.h): context, memory, CUDA-graph block
+// stepping, NCCL plumbing (dlopen'ed, so the library loads on a box without NCCL or a GPU),
+// host <-> device marshalling.  No CPU fallback anywhere: without a CUDA device al26_create fails.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>  // types only; every NCCL symbol is resolved with dlsym
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/al26_b200.h"
+#include "al26_internal.cuh"
+
+using namespace al26;
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::string g_create_error;
+
+bool load_nccl(std::string &why) {
+  if (g_nccl.ok) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) {
+    why = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+#define L(sym)                                                              \
+  *(void **)(&g_nccl.sym) = dlsym(g_nccl.h, "nccl" #sym);                   \
+  if (!g_nccl.sym) {                                                        \
+    why = "libnccl lacks nccl" #sym;                                        \
+    return false;                                                           \
+  }
+  L(GetUniqueId) L(CommInitRank) L(CommDestroy) L(AllGather) L(AllReduce) L(GroupStart) L(GroupEnd) L(GetErrorString)
+#undef L
+  g_nccl.ok = true;
+  return true;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct al26_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int clock_khz = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  double last_ms = 0.0;
+  int64_t last_launches = 0;
+  int64_t launches = 0;  // running counter of kernel launches (graph nodes included)
+
+  // dist
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+
+  // gravity
+  GravDev g{};
+  bool committed = false, dirty = true, in_evolve = false;
+  double t_model = 0.0, t_end_pending = 0.0;
+  double eps2 = 0.0, eta = 0.14, dt_max = 0.125, dt_min = 9.094947017729282e-13 /* 2^-40 */;
+  int64_t n_tot = 0;
+  int dbg_phase = 0;
+  cudaGraphExec_t graph = nullptr;
+  int graph_steps = 0;
+  bool graph_stale = false;  // parameters changed since the graph captured them by value
+  int expected_graph_launches = 1;
+  GravHeader *h_hdr = nullptr;  // pinned
+  double *scratch = nullptr;    // device staging, >= 16 * n_tot doubles
+  size_t scratch_doubles = 0;
+  double *en_scratch = nullptr;
+  size_t en_scratch_doubles = 0;
+  double *en_out = nullptr;  // device [3]
+  double *h_small = nullptr; // pinned [16]
+
+  // enrichment
+  EnrichDev e{};
+  bool e_committed = false;
+  double *e_glob = nullptr;     // device: mass, mdot, px..pvz (8 n), wr26, wr60, sn26, sn60 (4 n)
+  double *e_loc = nullptr;      // device: r_disk, tau (2 nloc), inv (8 nloc), fin (8 nloc)
+  uint8_t *e_flags = nullptr;   // device: kicked (n), alive (nloc)
+  int *e_ints = nullptr;        // device: counters[8], hm_list, sn_events
+  double4 *e_src = nullptr;     // device: src_a, src_b
+  int *h_events = nullptr;      // pinned [8 + ENR_MAX_SOURCES]
+  double km_per_length = 1.0, kms_per_speed = 1.0;
+};
+
+namespace {
+
+int fail(al26_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) return fail(c, AL26_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define NC(call)                                                                                       \
+  do {                                                                                                 \
+    ncclResult_t _r = (call);                                                                          \
+    if (_r != ncclSuccess) return fail(c, AL26_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(_r)); \
+  } while (0)
+
+double pow2floor_h(double x) {
+  int e;
+  frexp(x, &e);
+  return ldexp(1.0, e - 1);
+}
+
+// ---- small marshalling kernels ----
+__global__ void k_pack(int n, const double *m, const double *x, const double *y, const double *z, const double *vx,
+                       const double *vy, const double *vz, double4 *pos, double4 *vel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    pos[i] = make_double4(x[i], y[i], z[i], m[i]);
+    vel[i] = make_double4(vx[i], vy[i], vz[i], 0.0);
+  }
+}
+__global__ void k_unpack(int n, const double4 *pos, const double4 *vel, double *m, double *x, double *y, double *z,
+                         double *vx, double *vy, double *vz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double4 p = pos[i], v = vel[i];
+    x[i] = p.x; y[i] = p.y; z[i] = p.z; m[i] = p.w;
+    vx[i] = v.x; vy[i] = v.y; vz[i] = v.z;
+  }
+}
+__global__ void k_unpack_aj(int n, const double4 *acc, const double4 *jrk, double *out /*[7][n]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double4 a = acc[i], j = jrk[i];
+    out[0 * (size_t)n + i] = a.x; out[1 * (size_t)n + i] = a.y; out[2 * (size_t)n + i] = a.z;
+    out[3 * (size_t)n + i] = j.x; out[4 * (size_t)n + i] = j.y; out[5 * (size_t)n + i] = j.z;
+    out[6 * (size_t)n + i] = a.w;
+  }
+}
+__global__ void k_set_mass(int n, const double *m, double4 *pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[i].w = m[i];
+}
+__global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters) {
+  const int i = threadIdx.x;
+  if (i < 3) {
+    ctrl[i].t_next_bits = INF_BITS;
+    ctrl[i].n_act = 0;
+    ctrl[i].work_counter = 0;
+  }
+  if (i == 0 && zero_counters) {
+    hdr->n_steps = 0;
+    hdr->n_pairs = 0;
+    hdr->done = 0;
+  }
+}
+__global__ void k_reset_work(StepCtrl *ctrl) { ctrl->work_counter = 0; }
+__global__ void k_set_list(int n_act, const int *idx, int *list, StepCtrl *ctrl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_act) list[i] = idx[i];
+  if (i == 0) {
+    ctrl->n_act = n_act;
+    ctrl->work_counter = 0;
+  }
+}
+// scheduler parity hook: min(t+dt), then the list of particles that attain it
+__global__ void k_min_tnext(int n, const double *t, const double *dt, unsigned long long *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = INF_BITS;
+  if (i < n) v = (unsigned long long)__double_as_longlong(t[i] + dt[i]);
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  if ((threadIdx.x & 31) == 0 && v != INF_BITS) atomicMin(out, v);
+}
+__global__ void k_list_at(int n, const double *t, const double *dt, const unsigned long long *tn, int *list, int *cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (unsigned long long)__double_as_longlong(t[i] + dt[i]) == *tn) list[atomicAdd(cnt, 1)] = i;
+}
+
+inline int nblk(int64_t n, int t = 256) { return (int)((n + t - 1) / t); }
+
+int ensure_scratch(al26_ctx *c, size_t doubles) {
+  if (c->scratch_doubles >= doubles) return 0;
+  if (c->scratch) cudaFree(c->scratch);
+  c->scratch = nullptr;
+  c->scratch_doubles = 0;
+  CU(cudaMalloc(&c->scratch, doubles * sizeof(double)));
+  c->scratch_doubles = doubles;
+  return 0;
+}
+
+void free_gravity(al26_ctx *c) {
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  c->graph = nullptr;
+  GravDev &g = c->g;
+  void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  g = GravDev{};
+  c->committed = false;
+}
+
+void free_enrich(al26_ctx *c) {
+  void *ptrs[] = {c->e_glob, c->e_loc, c->e_flags, c->e_ints, c->e_src};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  c->e_glob = c->e_loc = nullptr;
+  c->e_flags = nullptr;
+  c->e_ints = nullptr;
+  c->e_src = nullptr;
+  c->e = EnrichDev{};
+  c->e_committed = false;
+}
+
+void slice_of(int64_t n, int rank, int world, int64_t &i0, int64_t &nloc) {
+  i0 = n * rank / world;
+  const int64_t i1 = n * (rank + 1) / world;
+  nloc = i1 - i0;
+}
+
+// all-gather the predicted / snapshot j-set; no-op on one GPU.  Slices are equal-sized
+// only when world divides n, so the gather is done as `world` broadcasts-by-allgather of the max
+// slice into a padded layout would waste bandwidth; instead require equal slices (n % world == 0
+// is enforced at commit) and use one in-place ncclAllGather per array.
+int gather_j(al26_ctx *c) {
+  if (c->world == 1) return 0;
+  const GravDev &g = c->g;
+  const size_t cnt = (size_t)g.n_loc * 4;  // doubles per rank
+  NC(g_nccl.GroupStart());
+  NC(g_nccl.AllGather(g.jpos + g.i0, g.jpos, cnt, ncclDouble, c->comm, c->stream));
+  NC(g_nccl.AllGather(g.jvel + g.i0, g.jvel, cnt, ncclDouble, c->comm, c->stream));
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+// global minimum of the next block time (one 8-byte all-reduce); no-op on one GPU
+int reduce_tnext(al26_ctx *c, int phase) {
+  if (c->world == 1) return 0;
+  unsigned long long *p = &c->g.ctrl[phase].t_next_bits;
+  NC(g_nccl.AllReduce(p, p, 1, ncclUint64, ncclMin, c->comm, c->stream));
+  return 0;
+}
+
+// one block step (or the init / sync variant) enqueued on the stream
+int enqueue_step(al26_ctx *c, int mode, int phase) {
+  c->launches += launch_predict_list(c->g, mode, phase, c->stream);
+  int rc = gather_j(c);
+  if (rc) return rc;
+  c->launches += launch_force(c->g, phase, c->stream);
+  c->launches += launch_correct(c->g, mode, phase, c->stream);
+  if (mode == MODE_STEP) {
+    rc = reduce_tnext(c, (phase + 1) % 3);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+constexpr int GRAPH_ROUNDS = 8;  // 3 phases x 8 = 24 block steps per graph launch
+
+int build_graph(al26_ctx *c) {
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  c->graph = nullptr;
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int64_t l0 = c->launches;
+  int rc = 0;
+  for (int r = 0; r < GRAPH_ROUNDS && !rc; r++)
+    for (int ph = 0; ph < 3 && !rc; ph++) rc = enqueue_step(c, MODE_STEP, ph);
+  c->launches = l0;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(c, AL26_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&c->graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(c, AL26_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  c->graph_steps = 3 * GRAPH_ROUNDS;
+  return 0;
+}
+
+int reset_ctrl(al26_ctx *c, int zero_counters) {
+  k_reset_ctrl<<<1, 32, 0, c->stream>>>(c->g.ctrl, c->g.hdr, zero_counters);
+  c->launches++;
+  return 0;
+}
+
+// forces + initial timesteps on every local particle (the "dirty" path)
+int initialise_forces(al26_ctx *c) {
+  reset_ctrl(c, 0);
+  int rc = enqueue_step(c, MODE_INIT, 0);
+  if (rc) return rc;
+  c->dirty = false;
+  return 0;
+}
+
+int read_header(al26_ctx *c) {
+  CU(cudaMemcpyAsync(c->h_hdr, c->g.hdr, sizeof(GravHeader), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int begin_evolve(al26_ctx *c, double t_end) {
+  if (!c->committed) return fail(c, AL26_ESTATE, "evolve before commit");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "evolve already in progress");
+  const double span = t_end - c->t_model;
+  if (!(span > 0.0)) return fail(c, AL26_ETIME, "t_end %.17g is not after model time %.17g", t_end, c->t_model);
+  c->g.eps2 = c->eps2; c->g.eta = c->eta; c->g.dt_max = c->dt_max; c->g.dt_min = c->dt_min;
+  int rc;
+  if (c->graph_stale) {
+    if ((rc = build_graph(c))) return rc;
+    c->graph_stale = false;
+  }
+  reset_ctrl(c, 1);  // zero this call's step / pair counters (the init force counts its pairs)
+  if (c->dirty && (rc = initialise_forces(c))) return rc;
+  double D = pow2floor_h(span);
+  if (D > c->dt_max) D = c->dt_max;
+  reset_ctrl(c, 0);
+  c->launches += launch_begin(c->g, span, D, c->stream);
+  if ((rc = reduce_tnext(c, 0))) return rc;
+  c->in_evolve = true;
+  c->t_end_pending = t_end;
+  c->dbg_phase = 0;
+  return 0;
+}
+
+int finish_evolve(al26_ctx *c) {
+  reset_ctrl(c, 0);
+  int rc = enqueue_step(c, MODE_SYNC, 0);
+  if (rc) return rc;
+  if ((rc = read_header(c))) return rc;
+  c->t_model = c->t_end_pending;
+  c->in_evolve = false;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int al26_version(void) { return 100; }
+
+const char *al26_last_error(al26_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+al26_ctx *al26_create(int device_id) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    fail(nullptr, AL26_ENODEV, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return nullptr;
+  }
+  if (device_id < 0 || device_id >= ndev) {
+    fail(nullptr, AL26_EINVAL, "device %d out of range (%d devices)", device_id, ndev);
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+    fail(nullptr, AL26_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (prop.major != 10) {
+    fail(nullptr, AL26_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major,
+         prop.minor);
+    return nullptr;
+  }
+  al26_ctx *c = new al26_ctx();
+  c->device = device_id;
+  c->sm_count = prop.multiProcessorCount;
+  c->clock_khz = prop.clockRate;
+  bool ok = cudaSetDevice(device_id) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
+            cudaMallocHost(&c->h_hdr, sizeof(GravHeader)) == cudaSuccess &&
+            cudaMallocHost(&c->h_small, 16 * sizeof(double)) == cudaSuccess &&
+            cudaMallocHost(&c->h_events, (8 + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&c->en_out, 4 * sizeof(double)) == cudaSuccess && force_kernel_setup() == cudaSuccess;
+  if (!ok) {
+    fail(nullptr, AL26_ECUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void al26_destroy(al26_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_gravity(c);
+  free_enrich(c);
+  if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->en_scratch) cudaFree(c->en_scratch);
+  if (c->en_out) cudaFree(c->en_out);
+  if (c->h_hdr) cudaFreeHost(c->h_hdr);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_events) cudaFreeHost(c->h_events);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int al26_device_info(al26_ctx *c, int *sm_count, int *clock_khz, int64_t *free_bytes, int64_t *total_bytes) {
+  if (!c) return AL26_EINVAL;
+  CU(cudaSetDevice(c->device));
+  size_t f = 0, t = 0;
+  CU(cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = c->sm_count;
+  if (clock_khz) *clock_khz = c->clock_khz;
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return 0;
+}
+
+int al26_dist_unique_id(void *out128) {
+  std::string why;
+  if (!out128) return AL26_EINVAL;
+  if (!load_nccl(why)) {
+    g_create_error = why;
+    return AL26_ENCCL;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) {
+    g_create_error = "ncclGetUniqueId failed";
+    return AL26_ENCCL;
+  }
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
+int al26_dist_init(al26_ctx *c, int rank, int world, const void *uid) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return fail(c, AL26_EINVAL, "bad rank/world %d/%d", rank, world);
+  if (c->committed || c->e_committed) return fail(c, AL26_ESTATE, "al26_dist_init must precede commit");
+  if (world == 1) {
+    c->rank = 0;
+    c->world = 1;
+    return 0;
+  }
+  if (!uid) return fail(c, AL26_EINVAL, "null nccl unique id");
+  std::string why;
+  if (!load_nccl(why)) return fail(c, AL26_ENCCL, "%s", why.c_str());
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, uid, sizeof(id));
+  NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  return 0;
+}
+
+int al26_grav_set_params(al26_ctx *c, double eps2, double eta, double dt_max, double dt_min) {
+  if (!c) return AL26_EINVAL;
+  if (!(eps2 >= 0.0) || !(eta > 0.0) || !(dt_max > 0.0) || !(dt_min > 0.0) || dt_min > dt_max)
+    return fail(c, AL26_EINVAL, "bad gravity parameters eps2=%g eta=%g dt_max=%g dt_min=%g", eps2, eta, dt_max, dt_min);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_params during evolve");
+  c->eps2 = eps2;
+  c->eta = eta;
+  c->dt_max = pow2floor_h(dt_max);
+  c->dt_min = pow2floor_h(dt_min);
+  c->dirty = true;
+  c->graph_stale = c->committed;
+  return 0;
+}
+
+int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, const double *y, const double *z,
+                     const double *vx, const double *vy, const double *vz) {
+  if (!c) return AL26_EINVAL;
+  if (n <= 0 || n > 0x7fffffff / 2) return fail(c, AL26_EINVAL, "particle count %lld out of range", (long long)n);
+  if (!m || !x || !y || !z || !vx || !vy || !vz) return fail(c, AL26_EINVAL, "null array");
+  if (n % c->world) return fail(c, AL26_EINVAL, "particle count %lld not divisible by world size %d", (long long)n, c->world);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "commit during evolve");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  free_gravity(c);
+  int64_t i0, nloc;
+  slice_of(n, c->rank, c->world, i0, nloc);
+  GravDev &g = c->g;
+  g.n_tot = (int)n; g.n_loc = (int)nloc; g.i0 = (int)i0;
+  g.grid_force = 2 * c->sm_count;
+  g.eps2 = c->eps2; g.eta = c->eta; g.dt_max = c->dt_max; g.dt_min = c->dt_min;
+  g.part_cap = part_capacity(g.n_loc, g.grid_force);
+  const size_t nl = (size_t)nloc, nt = (size_t)n;
+  CU(cudaMalloc(&g.pos, nl * sizeof(double4)));
+  CU(cudaMalloc(&g.vel, nl * sizeof(double4)));
+  CU(cudaMalloc(&g.acc, nl * sizeof(double4)));
+  CU(cudaMalloc(&g.jrk, nl * sizeof(double4)));
+  CU(cudaMalloc(&g.t, nl * sizeof(double)));
+  CU(cudaMalloc(&g.dt, nl * sizeof(double)));
+  CU(cudaMalloc(&g.jpos, nt * sizeof(double4)));
+  CU(cudaMalloc(&g.jvel, nt * sizeof(double4)));
+  CU(cudaMalloc(&g.list, nl * sizeof(int)));
+  CU(cudaMalloc(&g.part_a, (size_t)g.part_cap * sizeof(double4)));
+  CU(cudaMalloc(&g.part_j, (size_t)g.part_cap * sizeof(double4)));
+  CU(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
+  CU(cudaMalloc(&g.hdr, sizeof(GravHeader)));
+  CU(cudaMemsetAsync(g.acc, 0, nl * sizeof(double4), c->stream));
+  CU(cudaMemsetAsync(g.jrk, 0, nl * sizeof(double4), c->stream));
+  CU(cudaMemsetAsync(g.t, 0, nl * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(g.dt, 0, nl * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(g.hdr, 0, sizeof(GravHeader), c->stream));
+  int rc = ensure_scratch(c, 16 * nt);
+  if (rc) return rc;
+  const double *src[7] = {m, x, y, z, vx, vy, vz};
+  for (int k = 0; k < 7; k++)
+    CU(cudaMemcpyAsync(c->scratch + k * nl, src[k] + i0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  double *s = c->scratch;
+  k_pack<<<nblk(nloc), 256, 0, c->stream>>>((int)nloc, s, s + nl, s + 2 * nl, s + 3 * nl, s + 4 * nl, s + 5 * nl,
+                                            s + 6 * nl, g.pos, g.vel);
+  c->launches++;
+  reset_ctrl(c, 1);
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_tot = n;
+  c->committed = true;
+  c->dirty = true;
+  rc = build_graph(c);
+  if (rc) {
+    free_gravity(c);
+    return rc;
+  }
+  return 0;
+}
+
+int al26_grav_set_mass(al26_ctx *c, int64_t n, const double *m) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "set_mass before commit");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_mass during evolve");
+  if (n != c->n_tot || !m) return fail(c, AL26_EINVAL, "set_mass: n=%lld, committed %lld", (long long)n, (long long)c->n_tot);
+  CU(cudaSetDevice(c->device));
+  const size_t nl = (size_t)c->g.n_loc;
+  CU(cudaMemcpyAsync(c->scratch, m + c->g.i0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_set_mass<<<nblk(nl), 256, 0, c->stream>>>((int)nl, c->scratch, c->g.pos);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));  // the host buffer may be reused by the caller
+  c->dirty = true;
+  return 0;
+}
+
+int al26_grav_set_time(al26_ctx *c, double t) {
+  if (!c) return AL26_EINVAL;
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_time during evolve");
+  c->t_model = t;
+  return 0;
+}
+int al26_grav_get_time(al26_ctx *c, double *t) {
+  if (!c || !t) return AL26_EINVAL;
+  *t = c->t_model;
+  return 0;
+}
+
+int al26_grav_initialize(al26_ctx *c) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "initialize before commit");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "initialize during evolve");
+  CU(cudaSetDevice(c->device));
+  c->g.eps2 = c->eps2; c->g.eta = c->eta; c->g.dt_max = c->dt_max; c->g.dt_min = c->dt_min;
+  if (c->dirty) {
+    int rc = initialise_forces(c);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t *n_pairs) {
+  if (!c) return AL26_EINVAL;
+  if (n_block_steps) *n_block_steps = 0;
+  if (n_pairs) *n_pairs = 0;
+  if (c->committed && !c->in_evolve && t_end == c->t_model) return 0;
+  CU(cudaSetDevice(c->device));
+  const int64_t l0 = c->launches;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  int rc = begin_evolve(c, t_end);
+  if (rc) return rc;
+  int launches_needed = 0;
+  int batch = c->expected_graph_launches > 1 ? c->expected_graph_launches - 1 : 1;
+  while (true) {
+    for (int b = 0; b < batch; b++) {
+      CU(cudaGraphLaunch(c->graph, c->stream));
+      c->launches += 3 * c->graph_steps;
+      launches_needed++;
+    }
+    batch = 1;
+    if ((rc = read_header(c))) { c->in_evolve = false; return rc; }
+    if (c->h_hdr->done) break;
+  }
+  c->expected_graph_launches = launches_needed;
+  rc = finish_evolve(c);
+  if (rc) { c->in_evolve = false; return rc; }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_launches = c->launches - l0;
+  if (n_block_steps) *n_block_steps = c->h_hdr->n_steps;
+  if (n_pairs) *n_pairs = c->h_hdr->n_pairs;
+  return 0;
+}
+
+int al26_grav_dbg_begin(al26_ctx *c, double t_end) {
+  if (!c) return AL26_EINVAL;
+  CU(cudaSetDevice(c->device));
+  int rc = begin_evolve(c, t_end);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_dbg_advance(al26_ctx *c, int64_t max_steps, int64_t *n_done, int *finished) {
+  if (!c) return AL26_EINVAL;
+  if (!c->in_evolve) return fail(c, AL26_ESTATE, "dbg_advance outside begin/finish");
+  CU(cudaSetDevice(c->device));
+  int64_t done = 0;
+  int fin = 0;
+  while (max_steps < 0 || done < max_steps) {
+    int rc = read_header(c);
+    if (rc) return rc;
+    const long long before = c->h_hdr->n_steps;
+    if ((rc = enqueue_step(c, MODE_STEP, c->dbg_phase))) return rc;
+    if ((rc = read_header(c))) return rc;
+    if (c->h_hdr->done) {
+      // the step was a no-op; do not advance the phase: the no-op carried t_next forward into
+      // the next record, so keep rotating to stay consistent
+      c->dbg_phase = (c->dbg_phase + 1) % 3;
+      fin = 1;
+      break;
+    }
+    c->dbg_phase = (c->dbg_phase + 1) % 3;
+    done += c->h_hdr->n_steps - before;
+  }
+  if (n_done) *n_done = done;
+  if (finished) *finished = fin;
+  return 0;
+}
+
+int al26_grav_dbg_finish(al26_ctx *c) {
+  if (!c) return AL26_EINVAL;
+  if (!c->in_evolve) return fail(c, AL26_ESTATE, "dbg_finish outside begin");
+  CU(cudaSetDevice(c->device));
+  return finish_evolve(c);
+}
+
+int al26_grav_get_state(al26_ctx *c, int64_t n, double *m, double *x, double *y, double *z, double *vx, double *vy,
+                        double *vz) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "get_state before commit");
+  if (n != c->n_tot) return fail(c, AL26_EINVAL, "get_state: n=%lld, committed %lld", (long long)n, (long long)c->n_tot);
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  c->launches += launch_snapshot_j(g, c->stream);
+  int rc = gather_j(c);
+  if (rc) return rc;
+  const size_t nt = (size_t)n;
+  double *s = c->scratch;
+  k_unpack<<<nblk(n), 256, 0, c->stream>>>((int)n, g.jpos, g.jvel, s, s + nt, s + 2 * nt, s + 3 * nt, s + 4 * nt,
+                                           s + 5 * nt, s + 6 * nt);
+  c->launches++;
+  double *dst[7] = {m, x, y, z, vx, vy, vz};
+  for (int k = 0; k < 7; k++)
+    if (dst[k]) CU(cudaMemcpyAsync(dst[k], s + k * nt, nt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_get_acc_jerk(al26_ctx *c, int64_t n, double *ax, double *ay, double *az, double *jx, double *jy,
+                           double *jz, double *pot) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "get_acc_jerk before commit");
+  if (n != c->n_tot) return fail(c, AL26_EINVAL, "get_acc_jerk: size mismatch");
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  const size_t nl = (size_t)g.n_loc;
+  k_unpack_aj<<<nblk(nl), 256, 0, c->stream>>>((int)nl, g.acc, g.jrk, c->scratch);
+  c->launches++;
+  double *dst[7] = {ax, ay, az, jx, jy, jz, pot};
+  for (int k = 0; k < 7; k++)
+    if (dst[k])
+      CU(cudaMemcpyAsync(dst[k] + g.i0, c->scratch + k * nl, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_get_timesteps(al26_ctx *c, int64_t n, double *t, double *dt) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "get_timesteps before commit");
+  if (n != c->n_tot) return fail(c, AL26_EINVAL, "get_timesteps: size mismatch");
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  if (t) CU(cudaMemcpyAsync(t + g.i0, g.t, (size_t)g.n_loc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (dt) CU(cudaMemcpyAsync(dt + g.i0, g.dt, (size_t)g.n_loc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_set_timesteps(al26_ctx *c, int64_t n, const double *t, const double *dt) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "set_timesteps before commit");
+  if (n != c->n_tot || !t || !dt) return fail(c, AL26_EINVAL, "set_timesteps: size mismatch");
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  CU(cudaMemcpyAsync(g.t, t + g.i0, (size_t)g.n_loc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(g.dt, dt + g.i0, (size_t)g.n_loc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_grav_get_active(al26_ctx *c, int64_t cap, int32_t *idx, int64_t *n_active, double *tau_next) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "get_active before commit");
+  if (!idx || !n_active) return fail(c, AL26_EINVAL, "null output");
+  if (c->world != 1) return fail(c, AL26_ESTATE, "get_active is a single-GPU parity hook");
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  // scratch: [0] t_next bits, [1] count (as int), list after
+  unsigned long long *d_tn = reinterpret_cast<unsigned long long *>(c->scratch);
+  int *d_cnt = reinterpret_cast<int *>(c->scratch + 1);
+  int *d_list = reinterpret_cast<int *>(c->scratch + 2);
+  const unsigned long long inf = INF_BITS;
+  CU(cudaMemcpyAsync(d_tn, &inf, sizeof(inf), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(d_cnt, 0, sizeof(double), c->stream));
+  k_min_tnext<<<nblk(g.n_loc), 256, 0, c->stream>>>(g.n_loc, g.t, g.dt, d_tn);
+  k_list_at<<<nblk(g.n_loc), 256, 0, c->stream>>>(g.n_loc, g.t, g.dt, d_tn, d_list, d_cnt);
+  c->launches += 2;
+  unsigned long long tn_bits = 0;
+  int cnt = 0;
+  CU(cudaMemcpyAsync(&tn_bits, d_tn, sizeof(tn_bits), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (cnt > cap) return fail(c, AL26_ECAP, "active list of %d exceeds capacity %lld", cnt, (long long)cap);
+  CU(cudaMemcpy(idx, d_list, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+  std::sort(idx, idx + cnt);
+  *n_active = cnt;
+  if (tau_next) memcpy(tau_next, &tn_bits, sizeof(double));
+  return 0;
+}
+
+int al26_grav_get_last_active(al26_ctx *c, int64_t cap, int32_t *idx, int64_t *n_active) {
+  if (!c) return AL26_EINVAL;
+  if (!c->in_evolve) return fail(c, AL26_ESTATE, "get_last_active outside dbg_begin/dbg_finish");
+  if (!idx || !n_active) return fail(c, AL26_EINVAL, "null output");
+  CU(cudaSetDevice(c->device));
+  const int ph = (c->dbg_phase + 2) % 3;  // the step executed last
+  StepCtrl rec;
+  CU(cudaMemcpyAsync(&rec, &c->g.ctrl[ph], sizeof(rec), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (rec.n_act > cap) return fail(c, AL26_ECAP, "active list of %d exceeds capacity %lld", rec.n_act, (long long)cap);
+  CU(cudaMemcpy(idx, c->g.list, (size_t)rec.n_act * sizeof(int), cudaMemcpyDeviceToHost));
+  std::sort(idx, idx + rec.n_act);
+  for (int k = 0; k < rec.n_act; k++) idx[k] += c->g.i0;
+  *n_active = rec.n_act;
+  return 0;
+}
+
+int al26_grav_energies(al26_ctx *c, double *kinetic, double *potential, double *sum_mm_over_r) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "energies before commit");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "energies during evolve");
+  CU(cudaSetDevice(c->device));
+  const GravDev &g = c->g;
+  c->launches += launch_snapshot_j(g, c->stream);
+  int rc = gather_j(c);
+  if (rc) return rc;
+  const size_t need = (size_t)energy_grid(g.n_loc) * 3 + 2 * ((size_t)1184 * 256 + (size_t)g.n_loc + 512) + 64;
+  if (c->en_scratch_doubles < need) {
+    if (c->en_scratch) cudaFree(c->en_scratch);
+    c->en_scratch = nullptr;
+    c->en_scratch_doubles = 0;
+    CU(cudaMalloc(&c->en_scratch, need * sizeof(double)));
+    c->en_scratch_doubles = need;
+  }
+  EnergyDev e;
+  e.n_loc = g.n_loc; e.n_tot = g.n_tot; e.i0 = g.i0; e.eps2 = c->eps2;
+  e.pos = g.pos; e.vel = g.vel; e.jpos = g.jpos;
+  e.block_part = c->en_scratch; e.out = c->en_out;
+  c->launches += launch_energies(e, c->stream);
+  if (c->world > 1) NC(g_nccl.AllReduce(c->en_out, c->en_out, 3, ncclDouble, ncclSum, c->comm, c->stream));
+  CU(cudaMemcpyAsync(c->h_small, c->en_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (kinetic) *kinetic = c->h_small[0];
+  if (potential) *potential = c->h_small[1];
+  if (sum_mm_over_r) *sum_mm_over_r = c->h_small[2];
+  return 0;
+}
+
+int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const double *x, const double *y,
+                    const double *z, const double *vx, const double *vy, const double *vz, int64_t n_act,
+                    const int32_t *idx, double *ax, double *ay, double *az, double *jx, double *jy, double *jz,
+                    double *pot) {
+  if (!c) return AL26_EINVAL;
+  if (n <= 0 || n_act < 0 || n_act > n || !m || !x || !y || !z || !vx || !vy || !vz || (n_act && !idx))
+    return fail(c, AL26_EINVAL, "al26_grav_force: bad arguments");
+  if (n_act == 0) return 0;
+  for (int64_t k = 0; k < n_act; k++)
+    if (idx[k] < 0 || idx[k] >= n) return fail(c, AL26_EINVAL, "al26_grav_force: index %d out of range", idx[k]);
+  CU(cudaSetDevice(c->device));
+  GravDev g{};
+  g.n_loc = g.n_tot = (int)n; g.i0 = 0; g.grid_force = 2 * c->sm_count; g.eps2 = eps2;
+  g.part_cap = part_capacity((int)n, g.grid_force);
+  const size_t nt = (size_t)n, na = (size_t)n_act;
+  double *stage = nullptr;
+  int *d_idx = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+#define TRY(call) if (e == cudaSuccess) e = (call)
+  TRY(cudaMalloc(&stage, 7 * nt * sizeof(double)));
+  TRY(cudaMalloc(&g.jpos, nt * sizeof(double4)));
+  TRY(cudaMalloc(&g.jvel, nt * sizeof(double4)));
+  TRY(cudaMalloc(&g.list, nt * sizeof(int)));
+  TRY(cudaMalloc(&d_idx, na * sizeof(int)));
+  TRY(cudaMalloc(&g.part_a, (size_t)g.part_cap * sizeof(double4)));
+  TRY(cudaMalloc(&g.part_j, (size_t)g.part_cap * sizeof(double4)));
+  TRY(cudaMalloc(&g.raw_a, na * sizeof(double4)));
+  TRY(cudaMalloc(&g.raw_j, na * sizeof(double4)));
+  TRY(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
+  TRY(cudaMalloc(&g.hdr, sizeof(GravHeader)));
+  const double *src[7] = {m, x, y, z, vx, vy, vz};
+  for (int k = 0; k < 7; k++) TRY(cudaMemcpyAsync(stage + k * nt, src[k], nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TRY(cudaMemcpyAsync(d_idx, idx, na * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (e == cudaSuccess) {
+    k_pack<<<nblk(n), 256, 0, c->stream>>>((int)n, stage, stage + nt, stage + 2 * nt, stage + 3 * nt, stage + 4 * nt,
+                                           stage + 5 * nt, stage + 6 * nt, g.jpos, g.jvel);
+    k_reset_ctrl<<<1, 32, 0, c->stream>>>(g.ctrl, g.hdr, 1);
+    k_set_list<<<nblk(n_act), 256, 0, c->stream>>>((int)n_act, d_idx, g.list, g.ctrl);
+    launch_force(g, 0, c->stream);
+    launch_correct(g, MODE_RAW, 0, c->stream);
+    k_unpack_aj<<<nblk(n_act), 256, 0, c->stream>>>((int)n_act, g.raw_a, g.raw_j, stage);
+    c->launches += 6;
+    double *dst[7] = {ax, ay, az, jx, jy, jz, pot};
+    for (int k = 0; k < 7; k++)
+      if (dst[k]) TRY(cudaMemcpyAsync(dst[k], stage + k * na, na * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    TRY(cudaStreamSynchronize(c->stream));
+    TRY(cudaGetLastError());
+  }
+#undef TRY
+  if (e != cudaSuccess) rc = fail(c, AL26_ECUDA, "al26_grav_force: %s", cudaGetErrorString(e));
+  void *ptrs[] = {stage, g.jpos, g.jvel, g.list, d_idx, g.part_a, g.part_j, g.raw_a, g.raw_j, g.ctrl, g.hdr};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  return rc;
+}
+
+int al26_last_device_ms(al26_ctx *c, double *ms, int64_t *kernel_launches) {
+  if (!c) return AL26_EINVAL;
+  if (ms) *ms = c->last_ms;
+  if (kernel_launches) *kernel_launches = c->last_launches;
+  return 0;
+}
+
+int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_per_eval) {
+  if (!c) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "bench_force before commit");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "bench_force during evolve");
+  if (reps < 1) return fail(c, AL26_EINVAL, "reps must be >= 1");
+  CU(cudaSetDevice(c->device));
+  c->g.eps2 = c->eps2;
+  const int64_t l0 = c->launches;
+  reset_ctrl(c, 0);
+  c->launches += launch_predict_list(c->g, MODE_INIT, 0, c->stream);  // list = all, jpos = current
+  int rc = gather_j(c);
+  if (rc) return rc;
+  c->launches += launch_force(c->g, 0, c->stream);  // warm-up
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (int r = 0; r < reps; r++) {
+    k_reset_work<<<1, 1, 0, c->stream>>>(&c->g.ctrl[0]);
+    c->launches += 1 + launch_force(c->g, 0, c->stream);
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  CU(cudaGetLastError());
+  if (avg_ms) *avg_ms = (double)ms / reps;
+  if (pairs_per_eval) *pairs_per_eval = (int64_t)c->g.n_loc * (int64_t)c->g.n_tot;
+  c->last_ms = ms;
+  c->last_launches = c->launches - l0;
+  return 0;
+}
+
+// ---- enrichment ---------------------------------------------------------------------------
+
+int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const double *tau_disk_myr,
+                       const uint8_t *disk_alive, const uint8_t *kicked, const double *wr26, const double *wr60,
+                       const double *sn26, const double *sn60) {
+  if (!c) return AL26_EINVAL;
+  if (n <= 0 || n > 0x7fffffff / 2) return fail(c, AL26_EINVAL, "star count %lld out of range", (long long)n);
+  if (!r_disk_km || !tau_disk_myr || !disk_alive || !kicked || !wr26 || !wr60 || !sn26 || !sn60)
+    return fail(c, AL26_EINVAL, "null array");
+  if (n % c->world) return fail(c, AL26_EINVAL, "star count %lld not divisible by world size %d", (long long)n, c->world);
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  free_enrich(c);
+  int64_t d0, nloc;
+  slice_of(n, c->rank, c->world, d0, nloc);
+  const size_t nt = (size_t)n, nl = (size_t)nloc;
+  CU(cudaMalloc(&c->e_glob, 12 * nt * sizeof(double)));
+  CU(cudaMalloc(&c->e_loc, 18 * nl * sizeof(double)));
+  CU(cudaMalloc(&c->e_flags, nt + nl));
+  CU(cudaMalloc(&c->e_ints, (8 + 2 * ENR_MAX_SOURCES) * sizeof(int)));
+  CU(cudaMalloc(&c->e_src, 2 * ENR_MAX_SOURCES * sizeof(double4)));
+  EnrichDev &e = c->e;
+  e.n_tot = (int)n; e.d0 = (int)d0; e.n_loc = (int)nloc;
+  double *G = c->e_glob;
+  e.mass_msun = G; e.mdot = G + nt;
+  e.px = nullptr; e.py = e.pz = e.pvx = e.pvy = e.pvz = nullptr;
+  e.wr26 = G + 8 * nt; e.wr60 = G + 9 * nt; e.sn26 = G + 10 * nt; e.sn60 = G + 11 * nt;
+  double *Lc = c->e_loc;
+  e.r_disk = Lc; e.tau_disk = Lc + nl; e.inv = Lc + 2 * nl; e.fin = Lc + 10 * nl;
+  e.kicked = c->e_flags; e.alive = c->e_flags + nt;
+  e.counters = c->e_ints; e.hm_list = c->e_ints + 8; e.sn_events = c->e_ints + 8 + ENR_MAX_SOURCES;
+  e.src_a = c->e_src; e.src_b = c->e_src + ENR_MAX_SOURCES;
+  CU(cudaMemcpyAsync(G + 8 * nt, wr26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + 9 * nt, wr60, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + 10 * nt, sn26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + 11 * nt, sn60, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(Lc, r_disk_km + d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(Lc + nl, tau_disk_myr + d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(Lc + 2 * nl, 0, 16 * nl * sizeof(double), c->stream));
+  CU(cudaMemcpyAsync(c->e_flags, kicked, nt, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->e_flags + nt, disk_alive + d0, nl, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->e_committed = true;
+  return 0;
+}
+
+int al26_enrich_set_inventories(al26_ctx *c, int64_t n, const double *inv, const double *fin) {
+  if (!c) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_set_inventories before enrich_commit");
+  if (n != c->e.n_tot) return fail(c, AL26_EINVAL, "size mismatch");
+  CU(cudaSetDevice(c->device));
+  const size_t nl = (size_t)c->e.n_loc;
+  for (int r = 0; r < ENR_NINV; r++) {
+    if (inv) CU(cudaMemcpyAsync(c->e.inv + r * nl, inv + (size_t)r * n + c->e.d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (fin) CU(cudaMemcpyAsync(c->e.fin + r * nl, fin + (size_t)r * n + c->e.d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int al26_enrich_set_units(al26_ctx *c, double km_per_length, double kms_per_speed) {
+  if (!c) return AL26_EINVAL;
+  if (!(km_per_length > 0.0) || !(kms_per_speed > 0.0)) return fail(c, AL26_EINVAL, "unit factors must be positive");
+  c->km_per_length = km_per_length;
+  c->kms_per_speed = kms_per_speed;
+  return 0;
+}
+
+int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const double *mdot, const double *pos_vel,
+                     double dt_s, double t_new_myr, double r_bub_local_km, double r_bub_global_km, double decay26,
+                     double decay60, int with_agb, int32_t *sn_events, int64_t sn_cap, int64_t *n_sn_events) {
+  if (!c) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_step before enrich_commit");
+  if (n != c->e.n_tot || !mass_msun || !mdot) return fail(c, AL26_EINVAL, "enrich_step: size mismatch or null array");
+  if (!(r_bub_local_km > 0.0) || !(r_bub_global_km > 0.0)) return fail(c, AL26_EINVAL, "bubble radii must be positive");
+  if (!pos_vel && (!c->committed || c->n_tot != n))
+    return fail(c, AL26_ESTATE, "enrich_step with pos_vel == NULL needs a committed gravity state of the same size");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "enrich_step during evolve");
+  CU(cudaSetDevice(c->device));
+  const int64_t l0 = c->launches;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  const size_t nt = (size_t)n;
+  EnrichDev &e = c->e;
+  double *G = c->e_glob;
+  CU(cudaMemcpyAsync(G, mass_msun, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + nt, mdot, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (pos_vel) {
+    CU(cudaMemcpyAsync(G + 2 * nt, pos_vel, 6 * nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    e.px = G + 2 * nt; e.py = G + 3 * nt; e.pz = G + 4 * nt;
+    e.pvx = G + 5 * nt; e.pvy = G + 6 * nt; e.pvz = G + 7 * nt;
+    e.gpos = e.gvel = nullptr;
+  } else {
+    c->launches += launch_snapshot_j(c->g, c->stream);
+    int rc = gather_j(c);
+    if (rc) return rc;
+    e.px = e.py = e.pz = e.pvx = e.pvy = e.pvz = nullptr;
+    e.gpos = c->g.jpos;
+    e.gvel = c->g.jvel;
+    e.km_per_length = c->km_per_length;
+    e.kms_per_speed = c->kms_per_speed;
+  }
+  EnrichParams p;
+  p.dt_s = dt_s; p.t_new_myr = t_new_myr;
+  p.r_local = r_bub_local_km;
+  p.r_local3 = r_bub_local_km * (r_bub_local_km * r_bub_local_km);
+  p.r_global3 = r_bub_global_km * (r_bub_global_km * r_bub_global_km);
+  // smallest double q with sqrt(q) >= R: `R <= sqrt(d2)` <=> `d2 >= q` (sqrt is monotone and correctly rounded)
+  double q = r_bub_local_km * r_bub_local_km;
+  while (sqrt(q) >= r_bub_local_km) q = nextafter(q, -INFINITY);
+  while (sqrt(q) < r_bub_local_km) q = nextafter(q, INFINITY);
+  p.q_local = q;
+  p.decay26 = decay26; p.decay60 = decay60; p.with_agb = with_agb;
+  CU(cudaMemsetAsync(e.counters, 0, 8 * sizeof(int), c->stream));
+  c->launches += launch_enrich(e, p, c->stream);
+  CU(cudaMemcpyAsync(c->h_events, e.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_events + 8, e.sn_events, ENR_MAX_SOURCES * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_launches = c->launches - l0;
+  if (c->h_events[2]) return fail(c, AL26_ECAP, "more than %d massive stars", ENR_MAX_SOURCES);
+  const int ne = c->h_events[1];
+  if (n_sn_events) *n_sn_events = ne;
+  if (ne > 0) {
+    if (!sn_events || sn_cap < ne) return fail(c, AL26_ECAP, "%d supernova events exceed sn_cap %lld", ne, (long long)sn_cap);
+    memcpy(sn_events, c->h_events + 8, (size_t)ne * sizeof(int));
+  }
+  return 0;
+}
+
+int al26_enrich_get(al26_ctx *c, int64_t n, double *inv, double *fin, uint8_t *disk_alive, uint8_t *kicked) {
+  if (!c) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_get before enrich_commit");
+  if (n != c->e.n_tot) return fail(c, AL26_EINVAL, "size mismatch");
+  CU(cudaSetDevice(c->device));
+  const EnrichDev &e = c->e;
+  const size_t nl = (size_t)e.n_loc;
+  for (int r = 0; r < ENR_NINV; r++) {
+    if (inv) CU(cudaMemcpyAsync(inv + (size_t)r * n + e.d0, e.inv + r * nl, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (fin) CU(cudaMemcpyAsync(fin + (size_t)r * n + e.d0, e.fin + r * nl, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (disk_alive) CU(cudaMemcpyAsync(disk_alive + e.d0, e.alive, nl, cudaMemcpyDeviceToHost, c->stream));
+  if (kicked) CU(cudaMemcpyAsync(kicked, e.kicked, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""Build libal26b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python 26al-nbody_b200/csrc/build.py [--force] [--verbose]
+
+hermite_step.cu and enrich.cu are compiled with --fmad=false: their arithmetic has to follow
+the reference's / the oracle's evaluation order bit for bit (see the file headers).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libal26b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"] + ARCH
+UNITS = [
+    ("hermite_force.cu", []),
+    ("hermite_step.cu", ["--fmad=false"]),
+    ("enrich.cu", ["--fmad=false"]),
+    ("api.cu", []),
+]
+DEPS = ["al26_internal.cuh", os.path.join("..", "..", "include", "al26_b200.h")]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    deps = [os.path.join(HERE, d) for d in DEPS] + [os.path.abspath(__file__)]
+    for src, extra in UNITS:
+        s = os.path.join(HERE, src)
+        o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        os.makedirs(os.path.dirname(o), exist_ok=True)
+        if force or _newer(o, [s] + deps):
+            cmd = [nvcc] + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        objs.append(o)
+    if force or _newer(SO, objs):
+        cmd = [nvcc, "-shared", "-o", SO] + objs + ARCH + ["-ccbin", "/usr/bin/g++", "-ldl"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,206 @@
+// enrich.cu -- K5: the fused short-lived-radionuclide enrichment pass, one outer step of
+// /root/reference/al26_nbody.py:878-1086 (interloper block excluded):
+//   classify (:1194-1216) -> wind deposit, local + global bubble, 26Al + 60Fe (:642-702, :897-938)
+//   -> supernova events + deposit (:945-967, :1326-1334) -> decay (:1048-1064) -> condense (:1071-1086).
+// Compiled with --fmad=false and written in the reference's evaluation order, so the per-disc
+// wind sums are BIT-IDENTICAL to the reference's numba kernel: per disc the massive stars are
+// visited in ascending index order (the sorted source table), each term is
+// ((wind_ratio*mdot)*eta_bub)*dt with eta_bub = ((0.75*(r*r))*d_trav)/(R*(R*R)).
+// The reference evaluates the geometry four times per step (once per calc_wind_abs call); here
+// it is evaluated once per (disc, source) pair and feeds all four accumulators.
+//
+// Kernels (3 launches per outer step):
+//   k_enrich_classify  all stars: m >= 13 Msun -> atomic append to the source list
+//   k_enrich_sources   one CTA: bitonic sort of the list (ascending index), build the source
+//                      table {x,y,z,c26},{c60,sn26,sn60,event}, detect SN events (mdot == 0 and
+//                      not kicked), set kicked, emit the ordered event list
+//   k_enrich_discs     one thread per star of this rank's slice: source loop from shared memory
+//                      (broadcast reads), decay of all rows, condense flags; FP64-issue bound
+//                      for many sources, HBM bound (~260 B per disc-update) for few.
+#include "al26_internal.cuh"
+
+namespace al26 {
+
+constexpr int EN_T = 256;
+constexpr int SRC_TILE = 512;   // sources staged per shared-memory tile (2 x 16 KB)
+
+__global__ void __launch_bounds__(EN_T) k_enrich_classify(const EnrichDev e) {
+  const int i = blockIdx.x * EN_T + threadIdx.x;
+  if (i == 0) {
+    e.counters[1] = 0;
+  }
+  if (i >= e.n_tot) return;
+  if (e.mass_msun[i] >= 13.0) {
+    const int p = atomicAdd(&e.counters[0], 1);
+    if (p < ENR_MAX_SOURCES) e.hm_list[p] = i;
+    else e.counters[2] = 1;
+  }
+}
+
+__device__ __forceinline__ void star_pos(const EnrichDev &e, int i, double &x, double &y, double &z) {
+  if (e.px) {
+    x = e.px[i]; y = e.py[i]; z = e.pz[i];
+  } else {
+    const double4 p = e.gpos[i];
+    x = p.x * e.km_per_length; y = p.y * e.km_per_length; z = p.z * e.km_per_length;
+  }
+}
+__device__ __forceinline__ void star_vel(const EnrichDev &e, int i, double &x, double &y, double &z) {
+  if (e.px) {
+    x = e.pvx[i]; y = e.pvy[i]; z = e.pvz[i];
+  } else {
+    const double4 p = e.gvel[i];
+    x = p.x * e.kms_per_speed; y = p.y * e.kms_per_speed; z = p.z * e.kms_per_speed;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_enrich_sources(const EnrichDev e) {
+  __shared__ int keys[ENR_MAX_SOURCES];
+  int n_hm = e.counters[0];
+  if (n_hm > ENR_MAX_SOURCES) n_hm = ENR_MAX_SOURCES;
+  int np2 = 1;
+  while (np2 < n_hm) np2 <<= 1;
+  for (int k = threadIdx.x; k < np2; k += blockDim.x) keys[k] = (k < n_hm) ? e.hm_list[k] : 0x7fffffff;
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int k = threadIdx.x; k < np2; k += blockDim.x) {
+        const int partner = k ^ stride;
+        if (partner > k) {
+          const bool up = ((k & size) == 0);
+          const int a = keys[k], b = keys[partner];
+          if ((a > b) == up) {
+            keys[k] = b;
+            keys[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = threadIdx.x; k < n_hm; k += blockDim.x) {
+    const int i = keys[k];
+    e.hm_list[k] = i;
+    double x, y, z;
+    star_pos(e, i, x, y, z);
+    const double mdot = e.mdot[i];
+    const bool ev = (mdot == 0.0) && (e.kicked[i] == 0);
+    e.src_a[k] = make_double4(x, y, z, e.wr26[i] * mdot);
+    e.src_b[k] = make_double4(e.wr60[i] * mdot, ev ? e.sn26[i] : 0.0, ev ? e.sn60[i] : 0.0, ev ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ne = 0;
+    for (int k = 0; k < n_hm; k++) {
+      if (e.src_b[k].w != 0.0) {
+        const int i = keys[k];
+        e.sn_events[ne++] = i;
+        e.kicked[i] = 1;
+      }
+    }
+    e.counters[1] = ne;
+    e.counters[3] = n_hm;
+  }
+}
+
+__global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const EnrichParams p) {
+  __shared__ double4 sa[SRC_TILE];
+  __shared__ double4 sb[SRC_TILE];
+  const int li = blockIdx.x * EN_T + threadIdx.x;
+  const bool valid = li < e.n_loc;
+  const int gi = e.d0 + (valid ? li : 0);
+  int n_hm = e.counters[0];
+  if (n_hm > ENR_MAX_SOURCES) n_hm = ENR_MAX_SOURCES;
+  const int n_ev = e.counters[1];
+
+  const double m = valid ? e.mass_msun[gi] : 0.0;
+  const bool is_lm = valid && (m >= 0.1) && (m <= 3.0);
+  const size_t n = (size_t)e.n_loc;
+
+  double inv[ENR_NINV];
+#pragma unroll
+  for (int r = 0; r < ENR_NINV; r++) inv[r] = valid ? e.inv[r * n + li] : 0.0;
+
+  double x = 0, y = 0, z = 0, rd = 0, eta_l = 0, eta_g = 0;
+  if (is_lm && n_hm > 0) {
+    double vx, vy, vz;
+    star_pos(e, gi, x, y, z);
+    star_vel(e, gi, vx, vy, vz);
+    rd = e.r_disk[li];
+    const double spd = sqrt(vx * vx + vy * vy + vz * vz);   // (lm_vx**2 + lm_vy**2 + lm_vz**2)**0.5
+    const double trav = spd * p.dt_s;                       // d_disk_trav = disk_spd * dt
+    const double k0 = 0.75 * (rd * rd) * trav;              // 0.75 * (r_disk**2) * d_disk_trav
+    eta_l = k0 / p.r_local3;                                // / (bubble_radius ** 3)
+    eta_g = k0 / p.r_global3;
+  }
+  double l26 = 0.0, l60 = 0.0, g26 = 0.0, g60 = 0.0;
+  double s26 = inv[2], s60 = inv[6];  // SN deposits add straight onto the inventories (:964-965)
+
+  for (int b = 0; b < n_hm; b += SRC_TILE) {
+    const int cnt = min(SRC_TILE, n_hm - b);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt; k += EN_T) {
+      sa[k] = e.src_a[b + k];
+      sb[k] = e.src_b[b + k];
+    }
+    __syncthreads();
+    if (is_lm) {
+#pragma unroll 4
+      for (int k = 0; k < cnt; k++) {
+        const double4 A = sa[k];
+        const double4 B = sb[k];
+        // global model: distance_limit == 0 -> no test (:688)
+        g26 += (A.w * eta_g) * p.dt_s;
+        g60 += (B.x * eta_g) * p.dt_s;
+        // local model: skip when bubble_radius <= d_sep (:689-691); q_local is the exact
+        // d^2 threshold of that test, so no sqrt is needed here
+        const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (!(d2 >= p.q_local)) {
+          l26 += (A.w * eta_l) * p.dt_s;
+          l60 += (B.x * eta_l) * p.dt_s;
+        }
+        if (n_ev > 0 && B.w != 0.0) {
+          // calc_star_distance + calc_eta_disk_sne (:1331-1333)
+          const double d = sqrt(d2);
+          const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
+          s26 += B.y * eta;
+          s60 += B.z * eta;
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  // accumulate (:935-938), decay (:1054-1064)
+  inv[0] = (inv[0] + l26) * p.decay26;
+  inv[1] = (inv[1] + g26) * p.decay26;
+  inv[2] = s26 * p.decay26;
+  inv[4] = (inv[4] + l60) * p.decay60;
+  inv[5] = (inv[5] + g60) * p.decay60;
+  inv[6] = s60 * p.decay60;
+  if (p.with_agb) {
+    inv[3] *= p.decay26;
+    inv[7] *= p.decay60;
+  }
+#pragma unroll
+  for (int r = 0; r < ENR_NINV; r++) e.inv[r * n + li] = inv[r];
+  // condense (:1071-1086)
+  if (is_lm && e.alive[li]) {
+    const double tau = e.tau_disk[li];
+    if (tau >= p.t_new_myr) {
+#pragma unroll
+      for (int r = 0; r < ENR_NINV; r++)
+        if (p.with_agb || (r != 3 && r != 7)) e.fin[r * n + li] = inv[r];
+    }
+    if (tau < p.t_new_myr) e.alive[li] = 0;
+  }
+}
+
+int launch_enrich(const EnrichDev &e, const EnrichParams &p, cudaStream_t s) {
+  k_enrich_classify<<<(e.n_tot + EN_T - 1) / EN_T, EN_T, 0, s>>>(e);
+  k_enrich_sources<<<1, 1024, 0, s>>>(e);
+  k_enrich_discs<<<(e.n_loc + EN_T - 1) / EN_T, EN_T, 0, s>>>(e, p);
+  return 3;
+}
+
+}  // namespace al26

@@ -1,0 +1,334 @@
+// hermite_force.cu -- K1: softened fp64 pairwise acceleration + jerk + potential on the active
+// i-particles from the predicted j-set (stands in for ph4's
+// idata::get_acc_and_jerk behind gravity.evolve_model, al26_nbody.py:833), and K4's pair sums.
+//
+// Mapping (B200, sm_100a): FP64-pipe bound, 32 DP instructions per pair.
+//   * persistent grid (2 CTAs per SM), 256 threads = 8 warps per CTA;
+//   * a work item = (i-tile of 32*IPT active particles) x (one contiguous j-chunk); items are
+//     handed out by an atomic counter, so SMs stay busy for any n_act, and every item writes its
+//     own partial slot -> results do not depend on which CTA ran which item;
+//   * the 32 lanes of EVERY warp hold the item's i-particles (IPT per lane, in registers); the
+//     8 warps split the j's of each tile, and are summed in fixed warp order through shared
+//     memory at the end of the item -> bitwise reproducible run to run;
+//   * j-tiles ({x,y,z,m},{vx,vy,vz,-}: 64 B per j) are staged global -> shared by 1-D TMA bulk
+//     copies (cp.async.bulk + mbarrier complete_tx), 3 stages deep, issued by one thread;
+//     every lane reads the same j (shared-memory broadcast, LDS.128);
+//   * 1/sqrt: MUFU.RSQ64H seed + one 3rd-order step (5 DP ops), error ~1e-18 relative;
+//   * pairs with r^2 + eps2 == 0 (self, coincident) are masked on the integer pipe.
+// Tensor cores are not used: this is not a dense contraction.
+#include "al26_internal.cuh"
+
+namespace al26 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// 1/sqrt(x) for x >= 0; returns 0 for x == 0 (and sub-2^-1042 denormals): the self-pair mask.
+__device__ __forceinline__ double rsqrt_masked(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));  // MUFU.RSQ64H, ~2^-20 relative
+  // low word of y0 is zero; select on the high word only (integer pipe)
+  int hi = __double2hiint(x);
+  int yhi = (hi == 0) ? 0 : __double2hiint(y0);
+  y0 = __hiloint2double(yhi, 0);
+  const double y2 = y0 * y0;
+  const double e = fma(-x, y2, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double ye = y0 * e;
+  return fma(ye, p, y0);  // y0 (1 + e/2 + 3e^2/8): residual 5e^3/16
+}
+
+struct Acc7 {
+  double ax, ay, az, jx, jy, jz, pot;
+};
+
+__device__ __forceinline__ void pair_interaction(const double4 pj, const double4 vj, const double eps2,
+                                                 const double xi, const double yi, const double zi,
+                                                 const double vxi, const double vyi, const double vzi, Acc7 &s) {
+  const double dx = pj.x - xi, dy = pj.y - yi, dz = pj.z - zi;
+  const double dvx = vj.x - vxi, dvy = vj.y - vyi, dvz = vj.z - vzi;
+  const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+  const double rv = fma(dx, dvx, fma(dy, dvy, dz * dvz));
+  const double rinv = rsqrt_masked(r2);
+  const double rinv2 = rinv * rinv;
+  const double mrinv = pj.w * rinv;
+  const double mrinv3 = mrinv * rinv2;
+  const double al = (-3.0 * rv) * rinv2;
+  s.pot -= mrinv;
+  s.ax = fma(mrinv3, dx, s.ax);
+  s.ay = fma(mrinv3, dy, s.ay);
+  s.az = fma(mrinv3, dz, s.az);
+  s.jx = fma(mrinv3, fma(al, dx, dvx), s.jx);
+  s.jy = fma(mrinv3, fma(al, dy, dvy), s.jy);
+  s.jz = fma(mrinv3, fma(al, dz, dvz), s.jz);
+}
+
+struct ForceSmem {
+  double4 pos[FORCE_STAGES][FORCE_TJ];
+  double4 vel[FORCE_STAGES][FORCE_TJ];
+  double red[FORCE_WARPS][7][64];
+  unsigned long long full[FORCE_STAGES];
+  int item;
+};
+
+template <int IPT>
+__device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const Decomp &d, const int n_act,
+                                         const int item, uint32_t &it) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int itile = item / d.n_jsplit, js = item - itile * d.n_jsplit;
+  const int j0 = js * d.jchunk;
+  const int j1 = min(g.n_tot, j0 + d.jchunk);
+  const int ntiles = (j1 - j0 + FORCE_TJ - 1) / FORCE_TJ;
+
+  // producer prologue: all stages are free here (previous item ended with __syncthreads)
+  if (tid == 0) {
+    const int pre = ntiles < FORCE_STAGES ? ntiles : FORCE_STAGES;
+    for (int k = 0; k < pre; k++) {
+      const int st = (it + k) % FORCE_STAGES;
+      const int b = j0 + k * FORCE_TJ;
+      const int cnt = min(FORCE_TJ, j1 - b);
+      mbar_expect_tx(&sm.full[st], (uint32_t)cnt * 64u);
+      tma_load_1d(&sm.pos[st][0], g.jpos + b, (uint32_t)cnt * 32u, &sm.full[st]);
+      tma_load_1d(&sm.vel[st][0], g.jvel + b, (uint32_t)cnt * 32u, &sm.full[st]);
+    }
+  }
+
+  // my i-particles (identical in every warp)
+  double xi[IPT], yi[IPT], zi[IPT], vxi[IPT], vyi[IPT], vzi[IPT];
+  Acc7 s[IPT];
+#pragma unroll
+  for (int q = 0; q < IPT; q++) {
+    const int slot = itile * d.ti + q * 32 + lane;
+    const int li = (slot < n_act) ? g.list[slot] : g.list[0];
+    const double4 p = g.jpos[g.i0 + li];
+    const double4 v = g.jvel[g.i0 + li];
+    xi[q] = p.x; yi[q] = p.y; zi[q] = p.z;
+    vxi[q] = v.x; vyi[q] = v.y; vzi[q] = v.z;
+    s[q].ax = s[q].ay = s[q].az = s[q].jx = s[q].jy = s[q].jz = s[q].pot = 0.0;
+  }
+  const double eps2 = g.eps2;
+
+  for (int k = 0; k < ntiles; k++, it++) {
+    const int st = it % FORCE_STAGES;
+    const uint32_t parity = (it / FORCE_STAGES) & 1u;
+    const int cnt = min(FORCE_TJ, j1 - (j0 + k * FORCE_TJ));
+    mbar_wait(&sm.full[st], parity);
+    const double4 *__restrict__ sp = sm.pos[st];
+    const double4 *__restrict__ sv = sm.vel[st];
+#pragma unroll 2
+    for (int jj = warp; jj < cnt; jj += FORCE_WARPS) {
+      const double4 pj = sp[jj];
+      const double4 vj = sv[jj];
+#pragma unroll
+      for (int q = 0; q < IPT; q++) pair_interaction(pj, vj, eps2, xi[q], yi[q], zi[q], vxi[q], vyi[q], vzi[q], s[q]);
+    }
+    __syncthreads();  // every warp is done with stage st
+    if (tid == 0 && k + FORCE_STAGES < ntiles) {
+      const int b = j0 + (k + FORCE_STAGES) * FORCE_TJ;
+      const int c2 = min(FORCE_TJ, j1 - b);
+      mbar_expect_tx(&sm.full[st], (uint32_t)c2 * 64u);
+      tma_load_1d(&sm.pos[st][0], g.jpos + b, (uint32_t)c2 * 32u, &sm.full[st]);
+      tma_load_1d(&sm.vel[st][0], g.jvel + b, (uint32_t)c2 * 32u, &sm.full[st]);
+    }
+  }
+
+  // fixed-order reduction over the 8 warps
+#pragma unroll
+  for (int q = 0; q < IPT; q++) {
+    const int c = q * 32 + lane;
+    sm.red[warp][0][c] = s[q].ax; sm.red[warp][1][c] = s[q].ay; sm.red[warp][2][c] = s[q].az;
+    sm.red[warp][3][c] = s[q].jx; sm.red[warp][4][c] = s[q].jy; sm.red[warp][5][c] = s[q].jz;
+    sm.red[warp][6][c] = s[q].pot;
+  }
+  __syncthreads();
+  if (tid < d.ti) {
+    double r[7];
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+      double a = sm.red[0][c][tid];
+#pragma unroll
+      for (int w = 1; w < FORCE_WARPS; w++) a += sm.red[w][c][tid];
+      r[c] = a;
+    }
+    const long long o = (long long)js * d.slot_stride + (long long)itile * d.ti + tid;
+    g.part_a[o] = make_double4(r[0], r[1], r[2], r[6]);
+    g.part_j[o] = make_double4(r[3], r[4], r[5], 0.0);
+  }
+  // red[] is next written after at least one __syncthreads of the next item's tile loop
+  // (ntiles >= 1), or after the item-fetch barrier -> no hazard.
+}
+
+__global__ void __launch_bounds__(FORCE_THREADS, 2) k_force(const GravDev g, const int phase) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
+  StepCtrl *ctl = &g.ctrl[phase];
+  const int n_act = ctl->n_act;
+  if (n_act <= 0) return;
+  const Decomp d = make_decomp(n_act, g.n_tot, gridDim.x);
+  const int n_items = d.n_itiles * d.n_jsplit;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < FORCE_STAGES; s++) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  while (true) {
+    if (tid == 0) sm.item = atomicAdd(&ctl->work_counter, 1);
+    __syncthreads();
+    const int item = sm.item;
+    if (item >= n_items) break;
+    if (d.ipt == 2) run_item<2>(g, sm, d, n_act, item, it);
+    else run_item<1>(g, sm, d, n_act, item, it);
+    __syncthreads();
+  }
+}
+
+int force_smem_bytes() { return (int)sizeof(ForceSmem); }
+
+cudaError_t force_kernel_setup() {
+  return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmem));
+}
+
+int launch_force(const GravDev &g, int phase, cudaStream_t s) {
+  k_force<<<g.grid_force, FORCE_THREADS, sizeof(ForceSmem), s>>>(g, phase);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: pair sums for the energies: for local i over all j,
+//   u_i = sum_j m_j / sqrt(r^2 + eps2),  s_i = sum_j m_j / r   (self / coincident pairs masked)
+// then per-block partials of  K = 1/2 m v^2,  U = -1/2 m_i u_i,  S = 1/2 m_i s_i.
+// 2-D grid: x = i-tiles of 256, y = j-chunks; partials reduced in fixed order by k_energy_final.
+// ------------------------------------------------------------------------------------------
+constexpr int EN_THREADS = 256;
+constexpr int EN_TJ = 512;
+constexpr int EN_JSPLIT_TARGET = 1184;  // aim for ~8 CTAs per SM in total
+
+__global__ void __launch_bounds__(EN_THREADS) k_energy_pairs(const EnergyDev e, double *us_part, int n_jsplit,
+                                                             int jchunk) {
+  __shared__ double4 sj[EN_TJ];
+  const int i = blockIdx.x * EN_THREADS + threadIdx.x;
+  const bool valid = i < e.n_loc;
+  const double4 pi = e.jpos[e.i0 + (valid ? i : 0)];
+  const int j0 = blockIdx.y * jchunk, j1 = min(e.n_tot, j0 + jchunk);
+  double u = 0.0, s = 0.0;
+  const double eps2 = e.eps2;
+  const bool soft = eps2 != 0.0;
+  for (int b = j0; b < j1; b += EN_TJ) {
+    const int cnt = min(EN_TJ, j1 - b);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt; k += EN_THREADS) sj[k] = e.jpos[b + k];
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < cnt; k++) {
+      const double4 pj = sj[k];
+      const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+      const double ri = rsqrt_masked(r2);
+      s = fma(pj.w, ri, s);
+      if (soft) u = fma(pj.w, rsqrt_masked(r2 + eps2), u);
+    }
+  }
+  if (!soft) u = s;
+  if (valid) {
+    us_part[((long long)blockIdx.y * e.n_loc + i) * 2 + 0] = u;
+    us_part[((long long)blockIdx.y * e.n_loc + i) * 2 + 1] = s;
+  }
+  (void)n_jsplit;
+}
+
+__device__ __forceinline__ double block_sum_fixed(double v, double *sh) {
+  // fixed-order: butterfly in the warp, then warp 0 sums the warp totals in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
+  return r;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(EN_THREADS) k_energy_reduce(const EnergyDev e, const double *us_part, int n_jsplit) {
+  __shared__ double sh[EN_THREADS / 32];
+  const int i = blockIdx.x * EN_THREADS + threadIdx.x;
+  double K = 0.0, U = 0.0, S = 0.0;
+  if (i < e.n_loc) {
+    double u = 0.0, s = 0.0;
+    for (int js = 0; js < n_jsplit; js++) {
+      u += us_part[((long long)js * e.n_loc + i) * 2 + 0];
+      s += us_part[((long long)js * e.n_loc + i) * 2 + 1];
+    }
+    const double4 p = e.pos[i], v = e.vel[i];
+    K = 0.5 * p.w * fma(v.x, v.x, fma(v.y, v.y, v.z * v.z));
+    U = -0.5 * p.w * u;
+    S = 0.5 * p.w * s;
+  }
+  const double k = block_sum_fixed(K, sh);
+  const double u = block_sum_fixed(U, sh);
+  const double s = block_sum_fixed(S, sh);
+  if (threadIdx.x == 0) {
+    e.block_part[blockIdx.x * 3 + 0] = k;
+    e.block_part[blockIdx.x * 3 + 1] = u;
+    e.block_part[blockIdx.x * 3 + 2] = s;
+  }
+}
+
+__global__ void __launch_bounds__(EN_THREADS) k_energy_final(const EnergyDev e, int nblocks) {
+  __shared__ double sh[EN_THREADS / 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < nblocks; b += EN_THREADS)
+    for (int c = 0; c < 3; c++) acc[c] += e.block_part[b * 3 + c];
+  for (int c = 0; c < 3; c++) {
+    const double r = block_sum_fixed(acc[c], sh);
+    if (threadIdx.x == 0) e.out[c] = r;
+  }
+}
+
+int energy_grid(int n_loc) { return (n_loc + EN_THREADS - 1) / EN_THREADS; }
+
+// us_part scratch is carved from block_part's tail by the caller: see api.cu (energy_scratch_doubles)
+int launch_energies(const EnergyDev &e, cudaStream_t s) {
+  const int gx = energy_grid(e.n_loc);
+  int n_jsplit = (EN_JSPLIT_TARGET + gx - 1) / gx;
+  const int max_by_j = (e.n_tot + EN_TJ - 1) / EN_TJ;
+  if (n_jsplit > max_by_j) n_jsplit = max_by_j;
+  if (n_jsplit < 1) n_jsplit = 1;
+  if (n_jsplit > 65535) n_jsplit = 65535;
+  int jchunk = (e.n_tot + n_jsplit - 1) / n_jsplit;
+  n_jsplit = (e.n_tot + jchunk - 1) / jchunk;
+  double *us_part = e.block_part + (size_t)gx * 3;
+  k_energy_pairs<<<dim3(gx, n_jsplit), EN_THREADS, 0, s>>>(e, us_part, n_jsplit, jchunk);
+  k_energy_reduce<<<gx, EN_THREADS, 0, s>>>(e, us_part, n_jsplit);
+  k_energy_final<<<1, EN_THREADS, 0, s>>>(e, gx);
+  return 3;
+}
+
+}  // namespace al26

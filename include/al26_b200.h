@@ -1,0 +1,154 @@
+/* include/al26_b200.h -- C-ABI of libal26b200.so, the B200 (sm_100a) drop-in for the
+ * hot path of jweatson/26al-nbody.
+ *
+ * The reference has no C-ABI for this path: the boundary is a Python object protocol
+ * (AMUSE GravitationalDynamics, driven over RPC to MPI workers) plus in-process numpy /
+ * numba code.  Each entry point below names the reference interface it stands in for
+ * (file:line in /root/reference).  The Python host shim (26al-nbody_b200/gravity.py,
+ * enrichment.py) binds these with ctypes and re-creates the reference-side surface;
+ * INTEGRATION.md shows the stub a maintainer adds to al26_nbody.py.
+ *
+ * Conventions
+ *   - every pointer is a HOST pointer to a caller-owned, contiguous array; the library
+ *     copies in / out; device memory is library-owned;
+ *   - every function returns 0 on success, a negative AL26_E* code on failure, and
+ *     never aborts; al26_last_error() gives the message of the last failure;
+ *   - one context = one GPU = one host thread at a time; multi-GPU = one process and one
+ *     context per GPU, joined by al26_dist_init() (NCCL over NVLink);
+ *   - gravity works in N-body units, G = 1; enrichment works in the units of the
+ *     reference's numba kernel call (km, km/s, kg/s, s, kg; al26_nbody.py:886-895,904-905);
+ *   - there is NO CPU fallback: with no usable CUDA device al26_create() fails.
+ */
+#ifndef AL26_B200_H
+#define AL26_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct al26_ctx al26_ctx;
+
+enum {
+  AL26_OK = 0,
+  AL26_EINVAL = -1,   /* bad argument (size mismatch, negative parameter, null pointer) */
+  AL26_ESTATE = -2,   /* call not legal in the current state (e.g. evolve before commit) */
+  AL26_ETIME = -3,    /* t_end earlier than model time */
+  AL26_ECAP = -4,     /* caller buffer too small / internal capacity exceeded */
+  AL26_ECUDA = -5,    /* CUDA runtime error (message holds the CUDA error string) */
+  AL26_ENCCL = -6,    /* NCCL error or NCCL not loadable */
+  AL26_ENODEV = -7    /* no sm_100 device */
+};
+
+#define AL26_NINV 8 /* inventory rows: local26, global26, sne26, agb26, local60, global60, sne60, agb60
+                       (cluster.mass_{26al,60fe}_{local,global,sne,agb}, al26_nbody.py:1556-1577) */
+
+/* ---- context -------------------------------------------------------------------------
+ * replaces: the worker constructors `ph4(converter, number_of_workers=workers)` /
+ * `Hermite(...)` / `BHTree(...)` (al26_nbody.py:1709-1722) and `gravity.stop()` (:1762). */
+al26_ctx *al26_create(int device_id);
+void al26_destroy(al26_ctx *ctx);
+const char *al26_last_error(al26_ctx *ctx); /* ctx may be NULL: message of a failed al26_create */
+int al26_version(void);
+/* device info for the host shim / bench: SM count, clock (kHz), free and total bytes */
+int al26_device_info(al26_ctx *ctx, int *sm_count, int *clock_khz, int64_t *free_bytes, int64_t *total_bytes);
+
+/* ---- multi-GPU: i-particles and discs partitioned by contiguous index range;
+ * every block step each rank predicts its own j-slice and the slices are all-gathered.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0 (al26_dist_unique_id) and
+ * broadcast by the host (torch.distributed).  replaces: `number_of_workers=8` MPI ranks of
+ * the reference's worker (al26_nbody.py:57,1711-1720). */
+int al26_dist_unique_id(void *out128);
+int al26_dist_init(al26_ctx *ctx, int rank, int world, const void *nccl_unique_id);
+
+/* ---- gravity -------------------------------------------------------------------------*/
+/* replaces: `gravity.parameters.epsilon_squared / timestep_parameter` (never set by the
+ * script; defaults eps2 = 0, eta = 0.14).  dt_max / dt_min are rounded down to powers of 2. */
+int al26_grav_set_params(al26_ctx *ctx, double eps2, double eta, double dt_max, double dt_min);
+/* replaces: `gravity.particles.add_particles(cluster)` (al26_nbody.py:1728).  n is the GLOBAL
+ * particle count; index order is preserved (the script checks keys by index, :781-783). */
+int al26_grav_commit(al26_ctx *ctx, int64_t n, const double *m, const double *x, const double *y,
+                     const double *z, const double *vx, const double *vy, const double *vz);
+/* replaces: `stel_to_grav.copy_attributes(["mass"])` (al26_nbody.py:871,874): legal between
+ * evolve calls; forces and timesteps are re-initialised at the next evolve. */
+int al26_grav_set_mass(al26_ctx *ctx, int64_t n, const double *m);
+/* replaces: `gravity.model_time` setter / getter (al26_nbody.py:763,1101,1736). */
+int al26_grav_set_time(al26_ctx *ctx, double t);
+int al26_grav_get_time(al26_ctx *ctx, double *t);
+/* replaces: `gravity.evolve_model(t_new)` (al26_nbody.py:833).  On return every particle is
+ * synchronised at t_end.  n_block_steps / n_pairs (may be NULL) count this call's block steps
+ * and (i,j) pair evaluations on this rank. */
+int al26_grav_evolve(al26_ctx *ctx, double t_end, int64_t *n_block_steps, int64_t *n_pairs);
+/* replaces: the bulk getters `gravity.particles.{mass,x,y,z,vx,vy,vz}`, `.copy()` and the
+ * channel `grav_to_clus.copy()` (al26_nbody.py:831,872,876,886-891). n = global count. */
+int al26_grav_get_state(al26_ctx *ctx, int64_t n, double *m, double *x, double *y, double *z,
+                        double *vx, double *vy, double *vz);
+/* replaces: `gravity.kinetic_energy`, `gravity.potential_energy` (plotting/al26_plot.py:288-289)
+ * and `cluster.virial_radius()` (al26_nbody.py:770): R_vir = M^2 / (2 * sum_mm_over_r), G = 1.
+ * sum_mm_over_r is the UNSOFTENED sum over pairs i<j of m_i m_j / r_ij. */
+int al26_grav_energies(al26_ctx *ctx, double *kinetic, double *potential, double *sum_mm_over_r);
+
+/* parity hooks (no reference counterpart; used by tests/ against oracle/) */
+int al26_grav_initialize(al26_ctx *ctx); /* forces + initial timesteps now, without advancing */
+int al26_grav_get_acc_jerk(al26_ctx *ctx, int64_t n, double *ax, double *ay, double *az, double *jx,
+                           double *jy, double *jz, double *pot);
+int al26_grav_get_timesteps(al26_ctx *ctx, int64_t n, double *t, double *dt);
+int al26_grav_set_timesteps(al26_ctx *ctx, int64_t n, const double *t, const double *dt);
+/* active set of the next block step, ascending index order (bit-exact), and its time */
+int al26_grav_get_active(al26_ctx *ctx, int64_t cap, int32_t *idx, int64_t *n_active, double *tau_next);
+/* the active list the DEVICE scheduler built for the block step executed last inside
+ * dbg_begin/dbg_finish (ballot compaction in the predict kernel), sorted ascending */
+int al26_grav_get_last_active(al26_ctx *ctx, int64_t cap, int32_t *idx, int64_t *n_active);
+/* stepwise evolve: begin(t_end); advance(max_steps) any number of times; finish() */
+int al26_grav_dbg_begin(al26_ctx *ctx, double t_end);
+int al26_grav_dbg_advance(al26_ctx *ctx, int64_t max_steps, int64_t *n_done, int *finished);
+int al26_grav_dbg_finish(al26_ctx *ctx);
+/* one force evaluation (K1) on caller arrays: acc, jerk, pot on the n_act listed particles */
+int al26_grav_force(al26_ctx *ctx, int64_t n, double eps2, const double *m, const double *x, const double *y,
+                    const double *z, const double *vx, const double *vy, const double *vz, int64_t n_act,
+                    const int32_t *idx, double *ax, double *ay, double *az, double *jx, double *jy,
+                    double *jz, double *pot);
+/* timing hook for bench.py: device time (ms) of the last al26_grav_evolve / al26_enrich_step,
+ * measured with CUDA events on the library's own stream, and kernels launched in it */
+int al26_last_device_ms(al26_ctx *ctx, double *ms, int64_t *kernel_launches);
+/* bench hook: time `reps` full force evaluations (all i x all j, K1 only) on the committed
+ * state with CUDA events on the library stream; returns average ms per evaluation */
+int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pairs_per_eval);
+
+/* ---- enrichment (state lives on the device between calls) ---------------------------*/
+/* replaces: the per-star cluster attributes set in init_cluster (al26_nbody.py:1543-1603):
+ * r_disk [km], tau_disk [Myr], disk_alive, kicked, wind_ratio_26al/60fe, sn_yield_26al/60fe [kg].
+ * n = global star count.  Inventories and finals start at zero (:1556-1577). */
+int al26_enrich_commit(al26_ctx *ctx, int64_t n, const double *r_disk_km, const double *tau_disk_myr,
+                       const uint8_t *disk_alive, const uint8_t *kicked, const double *wr26,
+                       const double *wr60, const double *sn26_kg, const double *sn60_kg);
+/* overwrite inventories / finals (checkpoint resume, al26_nbody.py:1641-1656); either may be NULL */
+int al26_enrich_set_inventories(al26_ctx *ctx, int64_t n, const double *inv /*[8][n]*/, const double *fin /*[8][n]*/);
+/* conversion applied when al26_enrich_step is given pos_vel == NULL and reads the gravity state
+ * in place: x_km = x_nbody * km_per_length, v_kms = v_nbody * kms_per_speed
+ * (replaces `.value_in(units.km)` / `.value_in(units.km/units.s)`, al26_nbody.py:886-891) */
+int al26_enrich_set_units(al26_ctx *ctx, double km_per_length, double kms_per_speed);
+/* replaces one pass of al26_nbody.py:878-1086 (interloper block excluded):
+ *   classify (:1194-1216) on mass_msun; 4x calc_wind_abs (:642-702, :897-938) with local bubble
+ *   r_bub_local_km (distance-tested) and global bubble r_bub_global_km (= virial radius, no
+ *   test); SN events (mdot == 0 and not kicked, :946-967) with calc_eta_disk_sne (:1326-1334);
+ *   decay by decay26 / decay60 (host computes exp() as :1050-1051); condense (:1071-1086).
+ * mass_msun: the masses the reference classifies on (cluster.mass before this step's stellar
+ * evolve, :767).  mdot: -wind_mass_loss_rate in kg/s (:892).  pos_vel: [6][n] x,y,z (km),
+ * vx,vy,vz (km/s), or NULL to use the gravity state.  with_agb != 0 also decays / condenses the
+ * agb rows (:1062-1064,:1080-1082).  sn_events receives the ascending indices of this step's
+ * supernovae (capacity sn_cap). */
+int al26_enrich_step(al26_ctx *ctx, int64_t n, const double *mass_msun, const double *mdot_kg_s,
+                     const double *pos_vel, double dt_s, double t_new_myr, double r_bub_local_km,
+                     double r_bub_global_km, double decay26, double decay60, int with_agb,
+                     int32_t *sn_events, int64_t sn_cap, int64_t *n_sn_events);
+/* replaces: reading cluster.mass_*_{local,global,sne,agb}[_final], disk_alive, kicked when
+ * yields / checkpoints are written (al26_nbody.py:1097-1105).  Any pointer may be NULL. */
+int al26_enrich_get(al26_ctx *ctx, int64_t n, double *inv /*[8][n]*/, double *fin /*[8][n]*/,
+                    uint8_t *disk_alive, uint8_t *kicked);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AL26_B200_H */

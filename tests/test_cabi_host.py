@@ -1,0 +1,132 @@
+"""CPU: the C-ABI library loads and exports every symbol include/al26_b200.h declares, fails loudly
+without a GPU, and the host-side shim logic (units, particles, channels, ICs) behaves."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.load()
+    text = open(pkg.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(al26_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    lib_mod = importlib.import_module("26al-nbody_b200._lib")
+    assert declared == set(lib_mod.SIGNATURES), "ctypes prototypes and header disagree"
+    assert L.al26_version() == 100
+
+
+def test_oracle_is_not_reachable_from_the_product(pkg):
+    root = os.path.dirname(pkg.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "libhermite_oracle" not in src, f
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.Al26Error) as ei:
+        pkg.Context(0)
+    assert "no CPU fallback" in str(ei.value)
+    with pytest.raises(pkg.Al26Error):
+        pkg.GravityCore()
+    with pytest.raises(pkg.Al26Error):
+        pkg.EnrichCore()
+
+
+def test_units_and_converter(pkg):
+    U = pkg.units
+    assert (1.0 | U.pc).value_in(U.km) == pytest.approx(3.08567758128e13)
+    assert (100.0 | U.au).value_in(U.km) == pytest.approx(1.49597870691e10)
+    assert (0.01 | U.Myr).value_in(U.s) == pytest.approx(0.01e6 * 365.242199 * 86400)
+    q = (3.0 | U.km) * 2.0 + (1.0 | U.m)
+    assert q.value_in(U.m) == pytest.approx(6001.0)
+    assert ((2.0 | U.kms) * (5.0 | U.s)).value_in(U.km) == pytest.approx(10.0)
+    with pytest.raises(ValueError):
+        (1.0 | U.kg).value_in(U.m)
+    assert (13.0 | U.MSun) >= (13.0 | U.MSun) and not ((2.9 | U.MSun) > (3.0 | U.MSun))
+    cv = U.nbody_to_si(1.0 | U.pc, 339.0 | U.MSun)
+    assert cv.time_si / (1e6 * U.YR_S) == pytest.approx(0.81, rel=0.02)  # ~0.81 Myr per N-body time unit
+    x = cv.length_to_si(np.array([1.0, 2.0]))
+    assert np.allclose(cv.length_to_nbody(x), [1.0, 2.0])
+    assert cv.time_to_nbody(cv.time_to_si(0.125)) == pytest.approx(0.125)
+    cv2 = U.nbody_to_si(339.0 | U.MSun, 1.0 | U.pc)  # argument order is free, as in AMUSE
+    assert cv2.time_si == cv.time_si
+
+
+def test_particles_and_channels(pkg):
+    U = pkg.units
+    P = pkg.Particles
+    a = P(5)
+    a.mass = np.arange(1.0, 6.0) | U.MSun
+    a.x = np.zeros(5) | U.pc
+    a.flag = np.zeros(5, dtype=bool)
+    b = P(5, keys=a.key.copy())
+    b.mass = np.zeros(5) | U.MSun
+    a.new_channel_to(b).copy_attributes(["mass"])
+    assert np.array_equal(b.mass.value_in(U.MSun), a.mass.value_in(U.MSun))
+    b.mass[2] = 10.0 | U.MSun
+    assert a.mass.value_in(U.MSun)[2] == 3.0  # copies, not views
+    a[1].flag = True
+    a[3].new_attr = 7.5 | U.kg
+    assert a.flag.tolist() == [False, True, False, False, False] and a.new_attr.value_in(U.kg)[3] == 7.5
+    c = a.copy()
+    c.x = np.ones(5) | U.pc
+    assert a.x.value_in(U.pc)[0] == 0.0
+    assert all(a[i].key == b[i].key for i in range(5))
+    with pytest.raises(ValueError):
+        a.new_channel_to(P(4)).copy()
+    # virial radius of an equal-mass pair at separation d is 2 d ... M^2/(2 m1 m2/d) = (2m)^2 d/(2 m^2) = 2d
+    p = P(2)
+    p.mass = np.ones(2) | U.kg
+    p.x = np.array([0.0, 3.0]) | U.m; p.y = np.zeros(2) | U.m; p.z = np.zeros(2) | U.m
+    assert p.virial_radius().value_in(U.m) == pytest.approx(6.0)
+
+
+def test_initial_conditions(pkg):
+    ic = pkg.ic
+    rng = np.random.default_rng(0)
+    m = ic.maschberger_masses(200000, rng)
+    assert 0.01 <= m.min() and m.max() <= 150.0 and m.max() >= 13.0
+    # SURVEY section 6 (reference sampler): 0.186 % >= 13 Msun, 48.2 % in [0.1, 3], mean 0.339 Msun
+    assert np.mean(m >= 13.0) == pytest.approx(0.00186, rel=0.2)
+    assert np.mean((m >= 0.1) & (m <= 3.0)) == pytest.approx(0.482, rel=0.03)
+    assert m.mean() == pytest.approx(0.339, rel=0.1)
+    mm, x, y, z, vx, vy, vz = ic.plummer(20000, np.random.default_rng(1))
+    assert abs(x.mean()) < 1e-12 and abs(vx.mean()) < 1e-12 and mm.sum() == pytest.approx(1.0)
+    k = 0.5 * np.sum(mm * (vx * vx + vy * vy + vz * vz))
+    assert k == pytest.approx(0.25, rel=0.05)
+    f = ic.fractal(300, np.random.default_rng(2), 1.6)
+    kf = 0.5 * np.sum(f[0] * (f[4] ** 2 + f[5] ** 2 + f[6] ** 2))
+    uf = ic._potential_energy_numpy(*f[:4])
+    assert uf == pytest.approx(-0.5, rel=1e-9) and kf / abs(uf) == pytest.approx(0.5, rel=1e-9)
+    tau = ic.disk_lifetimes(100000, np.random.default_rng(3))
+    assert tau.mean() == pytest.approx(2.885, rel=0.02)
+    c = ic.cluster(500, seed=3)
+    assert c["m"].sum() == pytest.approx(1.0) and len(c["x"]) == 500
+    with pytest.raises(ValueError):
+        ic.cluster(10, model="king")
+
+
+def test_decay_fractions_literal(pkg):
+    from oracle import enrich_oracle as eo
+    f26, f60 = pkg.decay_fractions(0.01)
+    assert (f26, f60) == eo.decay_fractions(0.01)  # same call as the reference (np.exp)
+    # SURVEY 8(c) golden; np.exp may differ by 1 ulp between SIMD dispatch paths
+    assert f26 == pytest.approx(0.99037925616650468, rel=3e-16) and f60 == pytest.approx(0.99733760048885856, rel=3e-16)

@@ -1,0 +1,202 @@
+"""GPU parity: the sm_100a gravity path (through the C-ABI) against the CPU oracle on identical
+seeded inputs.  Tolerances (BASELINE.json north_star): acc/jerk <= 1e-12 relative (summation-order
+differences only); integer work (active sets, timesteps on the dyadic ladder, step counts) bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import hermite as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def vec_rel(a, b):
+    """max_i |a_i - b_i| / |b_i| over 3-vectors given as lists of component arrays."""
+    a, b = np.stack(a), np.stack(b)
+    return np.max(np.linalg.norm(a - b, axis=0) / np.linalg.norm(b, axis=0))
+
+
+def make(pkg, n, seed, model="plummer"):
+    c = pkg.ic.cluster(n, seed=seed, model=model, require_massive=False)
+    return [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
+
+
+@pytest.fixture()
+def grav(pkg, ctx):
+    return pkg.GravityCore(ctx=ctx)
+
+
+@pytest.mark.parametrize("n", [2, 3, 33, 257, 1000, 4096])
+@pytest.mark.parametrize("eps2", [0.0, 1e-4])
+def test_force_parity(pkg, grav, n, eps2):
+    p = make(pkg, n, seed=n)
+    out = grav.force(*p, eps2=eps2)
+    ref = H.force(*p, eps2=eps2, long_double=True)
+    assert vec_rel(out[:3], ref[:3]) < TOL
+    assert vec_rel(out[3:6], ref[3:6]) < TOL
+    assert np.max(np.abs(out[6] - ref[6]) / np.abs(ref[6])) < TOL
+    m = p[0]
+    assert np.max(np.abs((m * np.stack(out[:3])).sum(axis=1))) < 1e-13 * np.abs(m * np.stack(out[:3])).sum()
+
+
+def test_force_subset_ragged_and_coincident(pkg, grav):
+    p = make(pkg, 3000, seed=5)
+    rng = np.random.default_rng(0)
+    for k in (1, 7, 31, 32, 33, 64, 65, 700, 2999):
+        idx = np.sort(rng.choice(3000, k, replace=False)).astype(np.int32)
+        out = grav.force(*p, idx=idx)
+        ref = H.force(*p, idx=idx, long_double=True)
+        assert vec_rel(out[:3], ref[:3]) < TOL and vec_rel(out[3:6], ref[3:6]) < TOL
+    # coincident pair with eps2 = 0 is masked like the self-interaction
+    p[1][10], p[2][10], p[3][10] = p[1][11], p[2][11], p[3][11]
+    out = grav.force(*p)
+    ref = H.force(*p, long_double=True)
+    assert np.all(np.isfinite(np.stack(out)))
+    assert vec_rel(out[:3], ref[:3]) < TOL
+    # large active set crossing the two-i-per-thread threshold
+    p = make(pkg, 5000, seed=6)
+    out = grav.force(*p)
+    ref = H.force(*p, long_double=True)
+    assert vec_rel(out[:3], ref[:3]) < TOL and vec_rel(out[3:6], ref[3:6]) < TOL
+
+
+def test_force_is_deterministic(pkg, grav):
+    p = make(pkg, 2500, seed=9)
+    a = grav.force(*p)
+    b = grav.force(*p)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("n,model", [(256, "plummer"), (1000, "plummer"), (512, "fractal")])
+def test_initialize_and_stepwise_parity(pkg, grav, n, model):
+    p = make(pkg, n, seed=n + 1, model=model)
+    o = H.HermiteOracle(n)
+    o.commit(*p)
+    grav.commit(*p)
+    o.initialize(); grav.initialize()
+    ga, oa = grav.get_acc_jerk(), o.get_acc_jerk()
+    assert vec_rel(ga[:3], oa[:3]) < TOL and vec_rel(ga[3:6], oa[3:6]) < TOL
+    assert np.array_equal(grav.get_timesteps()[1], o.get_timesteps()[1])  # initial dt on the ladder: bit-exact
+    gi, gt = grav.get_active(); oi, ot = o.get_active()
+    assert np.array_equal(gi, oi) and gt == ot
+    t_end = 0.02
+    o.begin(t_end); grav.begin(t_end)
+    for step in range(60):
+        oi, ot = o.get_active()
+        nd_o, fin_o = o.advance(1)
+        nd_g, fin_g = grav.advance(1)
+        assert fin_o == fin_g and nd_o == nd_g
+        if fin_o:
+            break
+        assert np.array_equal(grav.get_last_active(), oi), f"active set differs at block step {step}"
+        gt_, gdt = grav.get_timesteps(); ot_, odt = o.get_timesteps()
+        assert np.array_equal(gt_, ot_) and np.array_equal(gdt, odt), f"ladder differs at block step {step}"
+    o.advance(-1); grav.advance(-1)
+    o.finish(); grav.finish()
+    gs, os_ = grav.get_state(), o.get_state()
+    assert np.array_equal(gs[0], os_[0])
+    assert vec_rel(gs[1:4], os_[1:4]) < 1e-10 and vec_rel(gs[4:7], os_[4:7]) < 1e-10
+    assert grav.get_time() == t_end
+
+
+def test_evolve_matches_oracle_counts_and_energy(pkg, grav):
+    n = 1000
+    p = make(pkg, n, seed=3)
+    o = H.HermiteOracle(n); o.commit(*p)
+    grav.commit(*p)
+    k0, u0, s0 = grav.energies()
+    ok0, ou0, os0 = o.energies()
+    assert k0 == pytest.approx(ok0, rel=1e-13) and u0 == pytest.approx(ou0, rel=1e-12) and s0 == pytest.approx(os0, rel=1e-12)
+    steps_g = pairs_g = steps_o = pairs_o = 0
+    for k in range(1, 4):
+        a, b = grav.evolve(0.0125 * k)
+        c, d = o.evolve(0.0125 * k)
+        steps_g += a; pairs_g += b; steps_o += c; pairs_o += d
+    assert (steps_g, pairs_g) == (steps_o, pairs_o)  # integer work: bit-exact
+    gs, os_ = grav.get_state(), o.get_state()
+    assert vec_rel(gs[1:4], os_[1:4]) < 1e-9 and vec_rel(gs[4:7], os_[4:7]) < 1e-9
+    k1, u1, _ = grav.energies()
+    ok1, ou1, _ = o.energies()
+    de_g, de_o = ((k0 + u0) - (k1 + u1)) / (k1 + u1), ((ok0 + ou0) - (ok1 + ou1)) / (ok1 + ou1)
+    assert abs(de_g) < 1e-5 and abs(de_g) <= 2.0 * abs(de_o) + 1e-9  # dE/E no worse than the CPU path
+
+
+def test_set_mass_and_time_setter(pkg, grav):
+    n = 300
+    p = make(pkg, n, seed=8)
+    o = H.HermiteOracle(n); o.commit(*p)
+    grav.commit(*p)
+    grav.evolve(0.01); o.evolve(0.01)
+    m2 = p[0] * np.random.default_rng(1).uniform(0.9, 1.0, n)  # mass loss fed in every outer step (:874)
+    grav.set_mass(m2); o.set_mass(m2)
+    grav.set_time(7.0); o.set_time(7.0)
+    a = grav.evolve(7.01); b = o.evolve(7.01)
+    assert a == b and grav.get_time() == 7.01
+    gs, os_ = grav.get_state(), o.get_state()
+    assert np.array_equal(gs[0], m2)
+    assert vec_rel(gs[1:4], os_[1:4]) < 1e-9
+
+
+def test_kepler_known_answer_on_gpu(pkg, grav):
+    from test_oracle_hermite import two_body
+    m, *ps = two_body(0.5)
+    grav.set_params(eta=0.05)
+    grav.commit(m, *ps)
+    k0, u0, _ = grav.energies()
+    grav.evolve(2.0 * np.pi)
+    k1, u1, _ = grav.energies()
+    assert abs((k1 + u1) - (k0 + u0)) / abs(k0 + u0) < 2e-7
+    st = grav.get_state()
+    for a, b in zip(st[1:], ps):
+        assert np.max(np.abs(a - b)) < 2e-4
+    grav.set_params()
+
+
+def test_error_codes_and_edge_cases(pkg, ctx):
+    g = pkg.GravityCore(ctx=ctx)
+    p = make(pkg, 64, seed=1)
+    g.commit(*p)
+    with pytest.raises(pkg.Al26Error) as ei:
+        g.evolve(-1.0)
+    assert ei.value.code == -3
+    with pytest.raises(pkg.Al26Error) as ei:
+        g.set_mass(np.ones(63))
+    assert ei.value.code == -1
+    with pytest.raises(pkg.Al26Error) as ei:
+        g.set_params(eta=-1.0)
+    assert ei.value.code == -1
+    assert g.evolve(0.0) == (0, 0)  # t_end == model time: nothing to do
+    # a single particle moves on a straight line
+    g.commit(np.ones(1), np.zeros(1), np.zeros(1), np.zeros(1), np.array([1.0]), np.zeros(1), np.zeros(1))
+    g.set_time(0.0)
+    g.evolve(0.25)
+    st = g.get_state()
+    assert st[1][0] == pytest.approx(0.25, rel=1e-15) and st[4][0] == 1.0
+
+
+def test_full_size_properties_1e5(pkg, grav):
+    """BASELINE config 3 size: size-independent properties instead of an O(N^2) CPU reference."""
+    n = 100_000
+    p = make(pkg, n, seed=42)
+    grav.commit(*p)
+    grav.initialize()
+    a = grav.get_acc_jerk()
+    m = p[0]
+    for comps in (a[:3], a[3:6]):
+        v = m * np.stack(comps)
+        assert np.max(np.abs(v.sum(axis=1))) < 1e-12 * np.abs(v).sum()  # sum m a = sum m jerk = 0
+    k, u, s = grav.energies()
+    assert u == pytest.approx(0.5 * np.sum(m * a[6]), rel=1e-12)       # U = 1/2 sum m_i phi_i
+    assert u == pytest.approx(-s, rel=1e-14)
+    # a random sample of rows against the long-double oracle
+    idx = np.sort(np.random.default_rng(0).choice(n, 64, replace=False)).astype(np.int32)
+    ref = H.force(*p, idx=idx, long_double=True)
+    assert vec_rel([c[idx] for c in a[:3]], ref[:3]) < TOL and vec_rel([c[idx] for c in a[3:6]], ref[3:6]) < TOL
+    steps, pairs = grav.evolve(2.0 ** -12)
+    assert steps >= 1 and pairs >= n * n
+    t, dt = grav.get_timesteps()
+    assert np.all(t == 0.0) and np.all(np.log2(dt) == np.round(np.log2(dt)))
+    k1, u1, _ = grav.energies()
+    assert abs((k1 + u1) - (k + u)) / abs(k + u) < 1e-8

@@ -1,0 +1,143 @@
+"""CPU: analytic known-answer tests that anchor the Hermite oracle (parity against AMUSE ph4 is
+unpinned -- SURVEY 8c; these are the anchors named there)."""
+import numpy as np
+import pytest
+
+from oracle import hermite as H
+
+
+def two_body(e=0.0, m1=0.6, m2=0.4):
+    """Bound two-body orbit, a = 1, G = 1, centre of mass at rest; starts at apocentre."""
+    mt = m1 + m2
+    r = 1.0 + e
+    v = np.sqrt(mt * (1.0 - e) / (1.0 + e))
+    x = np.array([-m2 / mt * r, m1 / mt * r]); y = np.zeros(2); z = np.zeros(2)
+    vy = np.array([-m2 / mt * v, m1 / mt * v]); vx = np.zeros(2); vz = np.zeros(2)
+    return np.array([m1, m2]), x, y, z, vx, vy, vz
+
+
+def plummer_equal(n, seed):
+    import importlib
+    ic = importlib.import_module("26al-nbody_b200").ic
+    return ic.plummer(n, np.random.default_rng(seed))
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b))
+
+
+def test_force_double_vs_long_double_and_momentum():
+    m, x, y, z, vx, vy, vz = plummer_equal(1000, 0)
+    m = np.random.default_rng(1).uniform(0.1, 2.0, 1000) / 1000
+    fd = H.force(m, x, y, z, vx, vy, vz)
+    fl = H.force(m, x, y, z, vx, vy, vz, long_double=True)
+    a_d, a_l = np.stack(fd[:3]), np.stack(fl[:3])
+    assert np.max(np.linalg.norm(a_d - a_l, axis=0) / np.linalg.norm(a_l, axis=0)) < 1e-12
+    j_d, j_l = np.stack(fd[3:6]), np.stack(fl[3:6])
+    assert np.max(np.linalg.norm(j_d - j_l, axis=0) / np.linalg.norm(j_l, axis=0)) < 1e-12
+    assert rel(fd[6], fl[6]) < 1e-13
+    # sum m a = 0, sum m jerk = 0 to rounding
+    assert np.max(np.abs((m * a_l).sum(axis=1))) < 1e-13 * np.abs(m * a_l).sum()
+    assert np.max(np.abs((m * j_l).sum(axis=1))) < 1e-13 * np.abs(m * j_l).sum()
+
+
+def test_force_two_body_analytic_and_softening():
+    m = np.array([2.0, 3.0])
+    x = np.array([0.0, 2.0]); o = np.zeros(2)
+    vx = np.array([0.0, 0.0]); vy = np.array([0.0, 1.0])
+    ax, ay, az, jx, jy, jz, pot = H.force(m, x, o, o, vx, vy, o)
+    assert ax[0] == pytest.approx(3.0 / 4.0) and ax[1] == pytest.approx(-2.0 / 4.0)
+    assert jy[0] == pytest.approx(3.0 / 8.0) and jy[1] == pytest.approx(-2.0 / 8.0)
+    assert pot[0] == pytest.approx(-1.5) and pot[1] == pytest.approx(-1.0)
+    ax2 = H.force(m, x, o, o, vx, vy, o, eps2=5.0)[0]
+    assert ax2[0] == pytest.approx(3.0 * 2.0 / 27.0)
+    # coincident particles (r2 == 0, eps2 == 0) are masked, not NaN
+    out = H.force(np.ones(3), np.array([0.0, 0.0, 1.0]), np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3))
+    assert np.all(np.isfinite(np.stack(out))) and out[0][0] == pytest.approx(1.0)
+
+
+@pytest.mark.parametrize("e", [0.0, 0.5, 0.9])
+def test_kepler_orbit(e):
+    m, *ps = two_body(e)
+    o = H.HermiteOracle(2, eta=0.05)
+    o.commit(m, *ps)
+    k0, u0, _ = o.energies()
+    period = 2.0 * np.pi
+    o.evolve(period)
+    k1, u1, _ = o.energies()
+    assert abs((k1 + u1) - (k0 + u0)) / abs(k0 + u0) < 2e-7
+    st = o.get_state()
+    for a, b in zip(st[1:], ps):
+        assert np.max(np.abs(a - b)) < 2e-4  # back at the start after one period
+    # angular momentum
+    L0 = np.sum(m * (ps[0] * ps[4] - ps[1] * ps[3])); L1 = np.sum(st[0] * (st[1] * st[5] - st[2] * st[4]))
+    assert abs(L1 - L0) / abs(L0) < 1e-7
+    assert o.get_time() == period
+
+
+def test_fourth_order_convergence():
+    m, *ps = two_body(0.5)
+    errs = []
+    for eta in (0.08, 0.04):
+        o = H.HermiteOracle(2, eta=eta)
+        o.commit(m, *ps)
+        k0, u0, _ = o.energies()
+        o.evolve(2.0 * np.pi)
+        k1, u1, _ = o.energies()
+        errs.append(abs((k1 + u1) - (k0 + u0)))
+    # dt ~ eta; block quantisation makes the ratio lumpy: 4th order => ~16x, accept >= 6x
+    assert errs[0] / errs[1] > 6.0
+
+
+def test_block_step_invariants_and_stepwise_equals_evolve():
+    m, *ps = plummer_equal(256, 4)
+    a = H.HermiteOracle(256); a.commit(m, *ps)
+    b = H.HermiteOracle(256); b.commit(m, *ps)
+    t_end = 0.03
+    b.begin(t_end)
+    steps = 0
+    while True:
+        idx, tn = b.get_active()
+        t, dt = b.get_timesteps()
+        e = np.log2(dt)
+        assert np.all(e == np.round(e)) and np.all(dt <= 2.0 ** -5)
+        assert np.all(np.mod(t, dt) == 0.0)  # every particle sits on its own ladder
+        nd, fin = b.advance(1)
+        if fin:
+            break
+        steps += nd
+        t2, dt2 = b.get_timesteps()
+        assert np.all(t2[idx] == tn)
+        grew = dt2[idx] > dt[idx]
+        assert np.all(np.mod(tn, dt2[idx][grew]) == 0.0)  # doubling only when commensurate
+        assert np.all((dt2[idx] == dt[idx]) | (dt2[idx] == 2 * dt[idx]) | (dt2[idx] == dt[idx] / 2))
+    b.finish()
+    ns, npairs = a.evolve(t_end)
+    assert ns == steps + 1  # + the synchronisation step
+    for u, v in zip(a.get_state(), b.get_state()):
+        assert np.array_equal(u, v)
+    assert np.all(b.get_timesteps()[0] == 0.0) and b.get_time() == t_end
+
+
+def test_plummer_virial_identities():
+    m, *ps = plummer_equal(4000, 7)
+    o = H.HermiteOracle(4000); o.commit(m, *ps)
+    k, u, s = o.energies()
+    assert k == pytest.approx(0.25, rel=0.06) and u == pytest.approx(-0.5, rel=0.06)
+    assert 1.0 / (2.0 * s) == pytest.approx(1.0, rel=0.06)  # R_vir = M^2 / (2 S)
+    assert u == pytest.approx(-s, rel=1e-14)                # eps2 = 0
+
+
+def test_set_mass_reinitialises_and_time_setter():
+    m, *ps = plummer_equal(64, 2)
+    o = H.HermiteOracle(64); o.commit(m, *ps)
+    o.evolve(0.01)
+    o.set_mass(m)  # marks dirty: forces are recomputed from the corrected positions
+    o.initialize()
+    a0 = o.get_acc_jerk()[0].copy()
+    o.set_mass(2.0 * m)
+    o.set_time(5.0)
+    o.initialize()
+    assert np.allclose(o.get_acc_jerk()[0], 2.0 * a0, rtol=1e-12)
+    o.evolve(5.01)
+    assert o.get_time() == 5.01
