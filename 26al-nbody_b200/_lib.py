@@ -60,6 +60,7 @@ SIGNATURES = {
     "al26_grav_force": (C.c_int, [_VP, C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32] + [_D] * 7),
     "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
+    "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     "al26_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
@@ -139,6 +140,11 @@ class Context:
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
         self.chk(self.L.al26_dist_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p) if buf else None))
         self.rank, self.world = int(rank), int(world)
+
+    def fp64_peak_tflops(self):
+        tf = C.c_double(0)
+        self.chk(self.L.al26_bench_fp64_peak(self.h, C.byref(tf)))
+        return tf.value
 
     def last_device_ms(self):
         ms, nl = C.c_double(0), C.c_int64(0)

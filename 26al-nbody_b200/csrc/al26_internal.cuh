@@ -104,6 +104,7 @@ int launch_force(const GravDev &g, int phase, cudaStream_t s);
 int launch_correct(const GravDev &g, int mode, int phase, cudaStream_t s);
 int launch_snapshot_j(const GravDev &g, cudaStream_t s);  // jpos/jvel := current state (s = 0)
 int force_smem_bytes();
+double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
 cudaError_t force_kernel_setup();
 
 // energies (K4): per-rank partial sums over local i x all j

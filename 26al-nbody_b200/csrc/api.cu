@@ -361,6 +361,8 @@ int finish_evolve(al26_ctx *c) {
   reset_ctrl(c, 0);
   int rc = enqueue_step(c, MODE_SYNC, 0);
   if (rc) return rc;
+  // times are relative to the start of an evolve call: everybody is synchronised, so tau = 0
+  CU(cudaMemsetAsync(c->g.t, 0, (size_t)c->g.n_loc * sizeof(double), c->stream));
   if ((rc = read_header(c))) return rc;
   c->t_model = c->t_end_pending;
   c->in_evolve = false;
@@ -910,6 +912,29 @@ int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_
   if (pairs_per_eval) *pairs_per_eval = (int64_t)c->g.n_loc * (int64_t)c->g.n_tot;
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
+  return 0;
+}
+
+int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {
+  if (!c || !tflops) return AL26_EINVAL;
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_scratch(c, 1024);
+  if (rc) return rc;
+  launch_dfma_peak(c->sm_count, 2000, c->scratch, c->stream);  // warm-up
+  double best = 0.0;
+  for (int r = 0; r < 5; r++) {
+    CU(cudaEventRecord(c->ev0, c->stream));
+    const double flops = launch_dfma_peak(c->sm_count, 20000, c->scratch, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  *tflops = best;
   return 0;
 }
 

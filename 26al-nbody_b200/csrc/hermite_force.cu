@@ -210,6 +210,27 @@ __global__ void __launch_bounds__(FORCE_THREADS, 2) k_force(const GravDev g, con
 
 int force_smem_bytes() { return (int)sizeof(ForceSmem); }
 
+// DFMA-only microkernel: the measured FP64 roofline denominator.  8 independent
+// chains per thread, 512 threads x 2 CTAs per SM.
+__global__ void __launch_bounds__(512, 2) k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 123.456) out[0] = r;  // never true; keeps the chains alive
+}
+
+double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s) {
+  const int blocks = sm_count * 2, threads = 512;
+  k_dfma_peak<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9);
+  return 2.0 * (double)blocks * threads * 64.0 * (double)iters;  // flops of one launch
+}
+
 cudaError_t force_kernel_setup() {
   return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmem));
 }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_predict_list(const GravDev g, co
   if (i < g.n_loc) {
     const double4 p = g.pos[i], v = g.vel[i], a = g.acc[i], j = g.jrk[i];
     const double ti = g.t[i], dti = g.dt[i];
-    const double s = tn - ti;
+    const double s = (MODE == MODE_INIT) ? 0.0 : (tn - ti);  // init: predicted == current, whatever t holds
     const double s2 = s * s * 0.5, s3 = s * s * s * (1.0 / 6.0);
     double4 pp, pv;
     pp.x = p.x + v.x * s + a.x * s2 + j.x * s3;

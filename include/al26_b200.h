@@ -116,6 +116,10 @@ int al26_last_device_ms(al26_ctx *ctx, double *ms, int64_t *kernel_launches);
  * state with CUDA events on the library stream; returns average ms per evaluation */
 int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pairs_per_eval);
 
+/* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
+ * the roofline denominator of the force kernel */
+int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);
+
 /* ---- enrichment (state lives on the device between calls) ---------------------------*/
 /* replaces: the per-star cluster attributes set in init_cluster (al26_nbody.py:1543-1603):
  * r_disk [km], tau_disk [Myr], disk_alive, kicked, wind_ratio_26al/60fe, sn_yield_26al/60fe [kg].

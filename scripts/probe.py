@@ -1,0 +1,33 @@
+"""GPU probe: force-kernel rate, FP64 peak, evolve timings vs span (development aid, not the bench)."""
+import importlib, sys, os, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("26al-nbody_b200")
+ctx = pkg.Context(0)
+print("device", ctx.device_info())
+print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
+    c = pkg.ic.cluster(n, seed=0)
+    g = pkg.GravityCore(ctx=ctx)
+    g.set_time(0.0)
+    g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+    ms, pairs = g.bench_force(3)
+    print(f"N={n} full force: {ms:.3f} ms, {pairs/ms*1e-6:.1f} Gpairs/s, {pairs*60/ms*1e-9:.2f} TF/s(60 flop)")
+    t0 = time.perf_counter(); g.initialize(); print("initialize wall", time.perf_counter() - t0)
+    t, dt = g.get_timesteps()
+    e, cnt = np.unique(np.log2(dt), return_counts=True)
+    print("initial dt ladder:", dict(zip(e.astype(int).tolist(), cnt.tolist())))
+    k0, u0, s0 = g.energies()
+    tnow = 0.0
+    for lg in (-14, -12, -10, -8, -7):
+        span = 2.0 ** lg
+        tnow += span
+        t0 = time.perf_counter()
+        steps, pairs = g.evolve(tnow)
+        wall = time.perf_counter() - t0
+        ms, nl = g.last_device_ms()
+        print(f"  span 2^{lg}: {steps} block steps, {pairs:.3e} pairs, dev {ms:.2f} ms, wall {wall*1e3:.2f} ms, "
+              f"{pairs/ms*1e-6:.1f} Gpairs/s, {ms*1e3/max(steps,1):.1f} us/step, mean n_act {pairs/n/max(steps,1):.0f}, launches {nl}")
+        if wall > 60: break
+    k1, u1, _ = g.energies()
+    print("  dE/E", ((k0 + u0) - (k1 + u1)) / (k1 + u1), "t=", tnow)

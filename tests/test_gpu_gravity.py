@@ -24,7 +24,9 @@ def make(pkg, n, seed, model="plummer"):
 
 @pytest.fixture()
 def grav(pkg, ctx):
-    return pkg.GravityCore(ctx=ctx)
+    g = pkg.GravityCore(ctx=ctx)  # the session shares one context: reset its clock and parameters
+    g.set_time(0.0)
+    return g
 
 
 @pytest.mark.parametrize("n", [2, 3, 33, 257, 1000, 4096])
@@ -156,6 +158,7 @@ def test_kepler_known_answer_on_gpu(pkg, grav):
 
 def test_error_codes_and_edge_cases(pkg, ctx):
     g = pkg.GravityCore(ctx=ctx)
+    g.set_time(0.0)
     p = make(pkg, 64, seed=1)
     g.commit(*p)
     with pytest.raises(pkg.Al26Error) as ei:
