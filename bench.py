@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (BASELINE.json):
+
+    metric  : fp64 Hermite pair interactions/s at N=1e5 (BASELINE.json config 3:
+              N=100,000 Plummer cluster, Maschberger IMF, Hermite block timesteps)
+    step    : one `gravity.evolve_model(t + dt_outer)` with the reference's outer step
+              dt_outer = t_f/1000 = 0.01 Myr (al26_nbody.py:786,833) -- hundreds of block steps
+    value   : pairs / device time, inputs resident in HBM (CUDA events on the library's stream)
+    e2e     : the same step through the reference-facing C-ABI calls with HOST buffers: mass channel
+              in (al26_nbody.py:874) -> evolve_model (:833) -> bulk getters out (:876,886-891),
+              host<->device copies inside the timed region
+    roofline: the force kernel (K1) alone on a full N x N evaluation, 60 flop per pair, against the
+              DFMA-microkernel FP64 peak measured on the same GPU in this run
+    cpu_baseline / --impl reference: the CPU oracle (a restatement -- AMUSE ph4 itself is not
+              installable: no MPI, no network), all host cores, bounded sample of the same workload
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Under torchrun (N > 1) one rank per GPU; rank 0 prints ONE JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fp64 Hermite pair interactions/s at N=1e5"
+UNIT = "pairs/s"
+FLOP_PER_PAIR = 60.0  # acc + jerk + pot, GRAPE counting
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--dt-myr", type=float, default=0.01)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-enrich", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
+    return ap.parse_args()
+
+
+def workload(pkg, n, seed, dt_myr):
+    """Config 3: Plummer sphere, r_vir = 1 pc, Maschberger IMF; N-body units from nbody_to_si(Rc, M)."""
+    U = pkg.units
+    c = pkg.ic.cluster(n, seed=seed, model="plummer")
+    cv = U.nbody_to_si(1.0 | U.pc, float(c["m_msun"].sum()) | U.MSun)
+    span = cv.time_to_nbody(dt_myr | U.Myr)
+    return c, cv, span
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(pkg, c, span, pair_budget):
+    """The CPU oracle on the same ICs: initial full force + block steps until the pair budget."""
+    from oracle import hermite as H
+    n = len(c["m"])
+    o = H.HermiteOracle(n)
+    o.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+    t0 = time.perf_counter()
+    o.begin(span)
+    while o.counters()[1] < pair_budget:
+        nd, fin = o.advance(1)
+        if fin:
+            break
+    dt = time.perf_counter() - t0
+    steps, pairs = o.counters()
+    return pairs / dt, pairs, steps, dt, H.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port; kind 'port') on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # only the host-side IC / unit helpers are used here: the CUDA library is never loaded on this arm
+    pkg = importlib.import_module("26al-nbody_b200")
+    c, cv, span = workload(pkg, args.n, args.seed, args.dt_myr)
+    from oracle import hermite as H
+    n = args.n
+    o = H.HermiteOracle(n)
+    o.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+    t_end = [span]
+    o.begin(t_end[0])  # initial N^2 force: set-up, not timed (the GPU arm's steps do not re-initialise either)
+    budget = 2.0e9  # pairs per step: a bounded slice of the same block-step sequence
+
+    def one_step():
+        p0 = o.counters()[1]
+        t0 = time.perf_counter()
+        while o.counters()[1] - p0 < budget:
+            nd, fin = o.advance(1)
+            if fin:  # this outer step is complete: synchronise and start the next one, as the script's loop does
+                o.finish()
+                t_end[0] += span
+                o.begin(t_end[0])
+        return o.counters()[1] - p0, time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    pairs = secs = 0.0
+    for _ in range(args.steps):
+        a, b = one_step()
+        pairs += a; secs += b
+    value = pairs / secs
+    cores = H.num_threads()
+    sample = (f"oracle/hermite_oracle.c (Hermite-4 block-step restatement of ph4, OpenMP x{cores}), same N={n} ICs; "
+              f"each step = consecutive block steps until >= {budget:.0e} pairs")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"N={n} Plummer, Maschberger IMF, r_vir=1 pc, Hermite-4 block timesteps, eta=0.14, eps2=0",
+                       "outer_dt_myr": args.dt_myr},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def enrichment_numbers(pkg, ctx, rank, world, do_cpu):
+    """BASELINE config 5: 1000 massive stars x 1e6 discs, wind + SN deposit + decay + condense."""
+    n_disc, n_hm = 1_000_000, 1000
+    n = n_disc + n_hm
+    n -= n % max(world, 1)
+    rng = np.random.default_rng(5)
+    mass = np.full(n, 1.0)
+    hm = np.arange(0, n, n // n_hm)[:n_hm]
+    mass[hm] = 20.0
+    wr26 = np.zeros(n); wr60 = np.zeros(n); sn = np.zeros(n)
+    wr26[hm], wr60[hm], sn[hm] = 1e-5, 1e-7, 1e26
+    mdot = np.zeros(n); mdot[hm] = 1e16
+    pc_km = 3.08567758128e13
+    pv = np.concatenate([rng.normal(0, 1.0 * pc_km, (3, n)), rng.normal(0, 1.0, (3, n))])
+    rd = np.full(n, 1.49597870691e10)
+    tau = rng.exponential(2.885, n)
+    e = pkg.EnrichCore(ctx=ctx)
+    e.commit(rd, tau, np.ones(n), np.zeros(n), wr26, wr60, sn, sn)
+    f26, f60 = pkg.decay_fractions(0.01)
+    dt_s = 0.01 * 1e6 * 365.242199 * 86400
+    dev, wall = [], []
+    for k in range(6):
+        t0 = time.perf_counter()
+        e.step(mass, mdot, pv, dt_s, 0.01 * (k + 1), 0.1 * pc_km, 2.0 * pc_km, f26, f60)
+        wall.append(time.perf_counter() - t0)
+        dev.append(e.last_device_ms()[0])
+    dev_ms, wall_s = float(np.median(dev[2:])), float(np.median(wall[2:]))
+    n_loc = n // world
+    out = {"workload": "1000 massive x 1e6 discs, local+global wind, SN, decay, condense",
+           "disc_updates_per_s_e2e": n_loc * world / wall_s, "disc_updates_per_s_device": n_loc * world / (dev_ms * 1e-3),
+           "source_disc_pairs_per_s_device": n_hm * float(n_disc) / (dev_ms * 1e-3),
+           "device_ms_incl_h2d": dev_ms, "h2d_bytes_per_step": 8 * n * 8, "launches_per_step": e.last_device_ms()[1]}
+    if do_cpu and rank == 0:
+        from oracle import enrich_oracle as eo
+        ns = 50_000  # bounded sample of discs, all 1000 sources, the reference's 4 calls
+        lm = np.nonzero(mass == 1.0)[0][:ns]
+        t0 = time.perf_counter()
+        for wr, lim, rad in ((wr26, 0.0, 2.0 * pc_km), (wr60, 0.0, 2.0 * pc_km), (wr26, 0.1 * pc_km, 0.1 * pc_km),
+                             (wr60, 0.1 * pc_km, 0.1 * pc_km)):
+            eo.calc_wind_abs(lm, hm, *pv, mdot, wr, rd, lim, rad, dt_s)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ns / dt, "unit": "disc-updates/s", "cores": 1, "kind": "port",
+                               "sample": f"oracle/enrich_oracle.py (numpy restatement of calc_wind_abs x4), {ns} discs x 1000 sources"}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    pkg = importlib.import_module("26al-nbody_b200")
+    ctx = pkg.Context(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.n - args.n % world
+    c, cv, span = workload(pkg, n, args.seed, args.dt_myr)
+    p = [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
+    g = pkg.GravityCore(ctx=ctx)
+    g.commit(*p)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- roofline of the dominant kernel (K1 force), timed alone --------------------------------
+    peak_tf = ctx.fp64_peak_tflops()
+    f_ms, f_pairs = g.bench_force(5)
+    achieved_tf = f_pairs * FLOP_PER_PAIR / (f_ms * 1e-3) / 1e12
+    nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12
+    roofline = {"bound": "fp64", "kernel": "k_force (full N x N/P evaluation, timed alone)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": "DFMA-only microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "frac_of_nominal_37.2": achieved_tf / nominal_tf, "flop_per_pair": FLOP_PER_PAIR,
+                "pairs_per_launch": f_pairs, "ms_per_launch": f_ms, "traffic": None}
+
+    # ---- device-resident arm: K evolve calls, CUDA events on the library stream ----------------
+    k0, u0, _ = g.energies()
+    t_now = 0.0
+    for _ in range(args.warmup):
+        t_now += span
+        g.evolve(t_now)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    tot_ms = tot_pairs = 0.0
+    tot_steps = launches = 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t_now += span
+        steps, pairs = g.evolve(t_now)
+        ms, nl = g.last_device_ms()
+        tot_ms += allmax(ms)
+        tot_pairs += allsum(float(pairs))
+        tot_steps += steps
+        launches += nl
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    k1, u1, _ = g.energies()
+    de = ((k0 + u0) - (k1 + u1)) / (k1 + u1)
+    value = tot_pairs / (tot_ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in / out every step --------------------------------------
+    m_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    m_host.numpy()[:] = c["m"]
+    outs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(7)]
+    outs_np = [o.numpy() for o in outs]
+
+    def e2e_step():
+        nonlocal t_now
+        t_now += span
+        g.set_mass(m_host.numpy())       # stel_to_grav.copy_attributes(["mass"])   (:874)
+        s_, p_ = g.evolve(t_now)         # gravity.evolve_model(t_new)               (:833)
+        g.get_state(outs_np)             # grav_to_clus.copy() / bulk getters        (:876,886-891)
+        return s_, p_, g.last_device_ms()[1]
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e_pairs = 0.0
+    e_launch = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s_, p_, nl = e2e_step()
+        e_pairs += p_
+        e_launch += nl
+    barrier()
+    e_wall = allmax(time.perf_counter() - t0)
+    e_pairs = allsum(float(e_pairs))
+    e2e = {"value": e_pairs / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 7 * 8 * n,
+           "ms_per_step": 1e3 * e_wall / args.steps,
+           "note": "set_mass (dirty -> full re-initialisation, as the reference's per-step mass channel forces) + evolve + get_state"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"N={n} Plummer, Maschberger IMF, r_vir=1 pc, Hermite-4 block timesteps, eta=0.14, eps2=0 "
+                                   f"(BASELINE config 3); step = evolve_model(t + {args.dt_myr} Myr = {span:.5f} N-body)",
+                       "outer_dt_myr": args.dt_myr, "parallelism": f"i-partition x{world} + NCCL j all-gather" if world > 1 else "1 GPU",
+                       "l2": "256 MiB device write between timed steps (state is 20 MB < L2; kernel is FP64-bound)"},
+            "block_steps_per_step": tot_steps / args.steps, "pairs_per_step": tot_pairs / args.steps,
+            "wall_s_timed_region": wall, "dE_over_E": de, "t_end_nbody": t_now,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches + e_launch), "clocks": clocks}
+
+    if not args.no_enrich:
+        line["enrichment"] = enrichment_numbers(pkg, ctx, rank, world, do_cpu=not args.no_cpu)
+    if world == 1 and rank == 0 and not args.no_cpu:
+        v, pr, st, secs, cores = cpu_sample(pkg, c, span, args.cpu_pairs)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle/hermite_oracle.c (ph4-equivalent restatement, not AMUSE ph4), same ICs: initial "
+                                          f"N^2 force + {st} block steps = {pr:.3e} pairs in {secs:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

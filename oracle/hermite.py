@@ -56,6 +56,8 @@ def lib():
         L.orc_energies.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
         L.orc_force.argtypes = ([C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32, C.c_int] + [_D] * 7)
         L.orc_num_threads.restype = C.c_int
+        L.orc_counters.restype = None
+        L.orc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -154,6 +156,12 @@ class HermiteOracle:
         na, tn = C.c_int64(0), C.c_double(0)
         self._chk(self.L.orc_get_active(self.h, self.n, idx, C.byref(na), C.byref(tn)))
         return idx[: na.value].copy(), tn.value
+
+    def counters(self):
+        """(block steps, pair evaluations) since creation."""
+        s, p = C.c_int64(0), C.c_int64(0)
+        self.L.orc_counters(self.h, C.byref(s), C.byref(p))
+        return s.value, p.value
 
     def energies(self):
         k, u, s = C.c_double(0), C.c_double(0), C.c_double(0)
