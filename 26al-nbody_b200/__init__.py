@@ -12,6 +12,7 @@ from .particles import Particles, Channel  # noqa: F401
 from .gravity import GravityCore, B200Gravity  # noqa: F401
 from .enrichment import EnrichCore, decay_fractions, NINV, ROWS, ROW  # noqa: F401
 from . import ic  # noqa: F401
+from . import dist  # noqa: F401
 
 __all__ = ["units", "Al26Error", "Context", "Particles", "Channel", "GravityCore", "B200Gravity",
            "EnrichCore", "decay_fractions", "ic", "load", "dist_unique_id"]

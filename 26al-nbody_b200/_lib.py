@@ -60,6 +60,7 @@ SIGNATURES = {
     "al26_grav_force": (C.c_int, [_VP, C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32] + [_D] * 7),
     "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
+    "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),

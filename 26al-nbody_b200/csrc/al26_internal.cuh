@@ -59,8 +59,9 @@ constexpr int FORCE_WARPS = FORCE_THREADS / 32;
 constexpr int FORCE_TJ = 256;      // j per TMA tile (2 x 8 KB per stage)
 constexpr int FORCE_STAGES = 3;
 constexpr int FORCE_MIN_JCHUNK = 256;
-constexpr int FORCE_ITEMS_PER_CTA = 16;
-constexpr int FORCE_IPT2_MIN_NACT = 2048;  // above this, two i-particles per thread
+constexpr int FORCE_MAX_ROUNDS = 16;             // work items per CTA at most (load balance for big blocks)
+constexpr long long FORCE_ITEM_PAIRS = 250000;   // do not cut items finer than this many pairs (~150 us)
+constexpr int FORCE_IPT2_MIN_NACT = 2048;        // above this, two i-particles per thread
 
 struct Decomp {
   int ipt;          // i-particles per thread (1 or 2)
@@ -71,16 +72,24 @@ struct Decomp {
   int slot_stride;  // n_itiles * ti
 };
 
+// Items = n_itiles x n_jsplit, handed out dynamically.  Small blocks: one round, at most `grid` items
+// (every CTA gets one big item; per-item overhead -- TMA prologue, barrier, reduction -- is paid once).
+// Big blocks: up to FORCE_MAX_ROUNDS rounds so the tail of the last round stays small.  The item
+// count is kept just BELOW a multiple of the grid so the last round is full.
 __host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid) {
   Decomp d;
   d.ipt = (n_act >= FORCE_IPT2_MIN_NACT) ? 2 : 1;
   d.ti = 32 * d.ipt;
   d.n_itiles = (n_act + d.ti - 1) / d.ti;
   if (d.n_itiles < 1) d.n_itiles = 1;
-  int want = (FORCE_ITEMS_PER_CTA * grid + d.n_itiles - 1) / d.n_itiles;
+  const long long total = (long long)d.n_itiles * d.ti * (long long)n_tot;
+  long long rounds = total / ((long long)grid * FORCE_ITEM_PAIRS);
+  if (rounds < 1) rounds = 1;
+  if (rounds > FORCE_MAX_ROUNDS) rounds = FORCE_MAX_ROUNDS;
+  int ns = (int)((rounds * grid) / d.n_itiles);
   int max_by_j = n_tot / FORCE_MIN_JCHUNK;
   if (max_by_j < 1) max_by_j = 1;
-  int ns = want < max_by_j ? want : max_by_j;
+  if (ns > max_by_j) ns = max_by_j;
   if (ns < 1) ns = 1;
   int jc = (n_tot + ns - 1) / ns;
   jc = (jc + 7) & ~7;
@@ -94,7 +103,7 @@ __host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid) {
 
 // partial-buffer entries that cover every n_act in [0, n_loc]
 inline long long part_capacity(int n_loc, int grid) {
-  return (long long)n_loc + 128 + (long long)(FORCE_ITEMS_PER_CTA * grid + 1) * 64 * 2;
+  return (long long)n_loc + 128 + (long long)(FORCE_MAX_ROUNDS * grid + 1) * 64 * 2;
 }
 
 // ---- launchers (each enqueues on `s`; returns the number of kernels launched) ----

@@ -186,6 +186,10 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
   }
 }
 __global__ void k_reset_work(StepCtrl *ctrl) { ctrl->work_counter = 0; }
+__global__ void k_set_nact(StepCtrl *ctrl, int n_act) {
+  ctrl->n_act = n_act;
+  ctrl->work_counter = 0;
+}
 __global__ void k_set_list(int n_act, const int *idx, int *list, StepCtrl *ctrl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_act) list[i] = idx[i];
@@ -885,11 +889,12 @@ int al26_last_device_ms(al26_ctx *c, double *ms, int64_t *kernel_launches) {
   return 0;
 }
 
-int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_per_eval) {
+int al26_grav_bench_force_n(al26_ctx *c, int64_t n_act, int reps, double *avg_ms, int64_t *pairs_per_eval) {
   if (!c) return AL26_EINVAL;
   if (!c->committed) return fail(c, AL26_ESTATE, "bench_force before commit");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "bench_force during evolve");
   if (reps < 1) return fail(c, AL26_EINVAL, "reps must be >= 1");
+  if (n_act <= 0 || n_act > c->g.n_loc) n_act = c->g.n_loc;
   CU(cudaSetDevice(c->device));
   c->g.eps2 = c->eps2;
   const int64_t l0 = c->launches;
@@ -897,7 +902,8 @@ int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_
   c->launches += launch_predict_list(c->g, MODE_INIT, 0, c->stream);  // list = all, jpos = current
   int rc = gather_j(c);
   if (rc) return rc;
-  c->launches += launch_force(c->g, 0, c->stream);  // warm-up
+  k_set_nact<<<1, 1, 0, c->stream>>>(&c->g.ctrl[0], (int)n_act);
+  c->launches += 1 + launch_force(c->g, 0, c->stream);  // warm-up
   CU(cudaEventRecord(c->ev0, c->stream));
   for (int r = 0; r < reps; r++) {
     k_reset_work<<<1, 1, 0, c->stream>>>(&c->g.ctrl[0]);
@@ -909,10 +915,14 @@ int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   CU(cudaGetLastError());
   if (avg_ms) *avg_ms = (double)ms / reps;
-  if (pairs_per_eval) *pairs_per_eval = (int64_t)c->g.n_loc * (int64_t)c->g.n_tot;
+  if (pairs_per_eval) *pairs_per_eval = n_act * (int64_t)c->g.n_tot;
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
   return 0;
+}
+
+int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_per_eval) {
+  return al26_grav_bench_force_n(c, 0, reps, avg_ms, pairs_per_eval);
 }
 
 int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {

@@ -121,9 +121,10 @@ class GravityCore:
         self.ctx.chk(self.L.al26_grav_force(self.h, n, float(eps2), *arrs, len(idx), idx, *out))
         return out
 
-    def bench_force(self, reps=3):
+    def bench_force(self, reps=3, n_act=0):
+        """Average ms of one K1 launch with the first n_act (0: all) particles active, and its pairs."""
         ms, pairs = C.c_double(0), C.c_int64(0)
-        self.ctx.chk(self.L.al26_grav_bench_force(self.h, int(reps), C.byref(ms), C.byref(pairs)))
+        self.ctx.chk(self.L.al26_grav_bench_force_n(self.h, int(n_act), int(reps), C.byref(ms), C.byref(pairs)))
         return ms.value, pairs.value
 
     def last_device_ms(self):

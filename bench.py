@@ -238,11 +238,7 @@ def main():
     ctx = pkg.Context(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.dist_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        pkg.dist.init_context(ctx, rank, world, device="cuda")
 
     def barrier():
         if world > 1:

@@ -115,6 +115,8 @@ int al26_last_device_ms(al26_ctx *ctx, double *ms, int64_t *kernel_launches);
 /* bench hook: time `reps` full force evaluations (all i x all j, K1 only) on the committed
  * state with CUDA events on the library stream; returns average ms per evaluation */
 int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pairs_per_eval);
+/* same with only the first n_act (<= 0: all) local particles active: the small-block regime */
+int al26_grav_bench_force_n(al26_ctx *ctx, int64_t n_act, int reps, double *avg_ms, int64_t *pairs_per_eval);
 
 /* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
  * the roofline denominator of the force kernel */

@@ -13,6 +13,10 @@ for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
     g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
     ms, pairs = g.bench_force(3)
     print(f"N={n} full force: {ms:.3f} ms, {pairs/ms*1e-6:.1f} Gpairs/s, {pairs*60/ms*1e-9:.2f} TF/s(60 flop)")
+    for na in (1, 8, 32, 100, 300, 500, 1000, 2000, 2048, 5000, 20000):
+        if na > n: break
+        ms, pairs = g.bench_force(20, n_act=na)
+        print(f"   n_act={na:6d}: {ms*1e3:8.1f} us/launch (incl. ~2 us reset launch), {pairs/ms*1e-6:7.1f} Gpairs/s")
     t0 = time.perf_counter(); g.initialize(); print("initialize wall", time.perf_counter() - t0)
     t, dt = g.get_timesteps()
     e, cnt = np.unique(np.log2(dt), return_counts=True)
