@@ -61,6 +61,8 @@ SIGNATURES = {
     "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
+    "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),
+    "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
@@ -141,6 +143,14 @@ class Context:
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
         self.chk(self.L.al26_dist_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p) if buf else None))
         self.rank, self.world = int(rank), int(world)
+
+    def set_force_variant(self, v):
+        self.chk(self.L.al26_set_force_variant(self.h, int(v)))
+
+    def block_histogram(self):
+        h = (C.c_int64 * 32)()
+        self.chk(self.L.al26_grav_block_histogram(self.h, h))
+        return list(h)
 
     def fp64_peak_tflops(self):
         tf = C.c_double(0)

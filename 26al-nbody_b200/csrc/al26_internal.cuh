@@ -30,6 +30,7 @@ struct GravHeader {
   int pad;
   long long n_steps;  // block steps taken (this rank)
   long long n_pairs;  // (i,j) pair evaluations (this rank)
+  long long nact_hist[32];  // diagnostic: block steps by floor(log2(n_act)), since the last commit
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
@@ -39,6 +40,8 @@ struct GravDev {
   int n_tot;  // global particle count (the j-set)
   int i0;     // global index of local particle 0
   int grid_force;
+  int variant;    // force-kernel configuration (hermite_force.cu)
+  int force_ipt;  // its i-particles per lane for big blocks
   double eps2, eta, dt_max, dt_min;
   double4 *pos, *vel, *acc, *jrk;
   double *t, *dt;
@@ -54,17 +57,17 @@ struct GravDev {
 
 // ---- work decomposition of one force evaluation, a pure function of (n_act, n_tot, grid) so
 // the force kernel and the reduce/corrector kernel agree without communicating ----
-constexpr int FORCE_THREADS = 256;
-constexpr int FORCE_WARPS = FORCE_THREADS / 32;
 constexpr int FORCE_TJ = 256;      // j per TMA tile (2 x 8 KB per stage)
 constexpr int FORCE_STAGES = 3;
 constexpr int FORCE_MIN_JCHUNK = 256;
 constexpr int FORCE_MAX_ROUNDS = 16;             // work items per CTA at most (load balance for big blocks)
 constexpr long long FORCE_ITEM_PAIRS = 250000;   // do not cut items finer than this many pairs (~150 us)
-constexpr int FORCE_IPT2_MIN_NACT = 2048;        // above this, two i-particles per thread
+constexpr int FORCE_BIG_NACT_PER_IPT = 1024;      // n_act >= this x IPT: IPT i-particles per lane
+constexpr int FORCE_SPLIT_MAX_NACT = 16;         // n_act <= this: lanes split over j as well (tiny blocks)
+constexpr int FORCE_IPT_MAX = 4;
 
 struct Decomp {
-  int ipt;          // i-particles per thread (1 or 2)
+  int ipt;          // i-particles per lane (1, or the configuration's IPT for big blocks)
   int ti;           // i per work item = 32 * ipt
   int n_itiles;
   int n_jsplit;
@@ -76,9 +79,9 @@ struct Decomp {
 // (every CTA gets one big item; per-item overhead -- TMA prologue, barrier, reduction -- is paid once).
 // Big blocks: up to FORCE_MAX_ROUNDS rounds so the tail of the last round stays small.  The item
 // count is kept just BELOW a multiple of the grid so the last round is full.
-__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid) {
+__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid, int ipt_big) {
   Decomp d;
-  d.ipt = (n_act >= FORCE_IPT2_MIN_NACT) ? 2 : 1;
+  d.ipt = (n_act >= FORCE_BIG_NACT_PER_IPT * ipt_big) ? ipt_big : 1;
   d.ti = 32 * d.ipt;
   d.n_itiles = (n_act + d.ti - 1) / d.ti;
   if (d.n_itiles < 1) d.n_itiles = 1;
@@ -103,7 +106,7 @@ __host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid) {
 
 // partial-buffer entries that cover every n_act in [0, n_loc]
 inline long long part_capacity(int n_loc, int grid) {
-  return (long long)n_loc + 128 + (long long)(FORCE_MAX_ROUNDS * grid + 1) * 64 * 2;
+  return (long long)n_loc + 32 * FORCE_IPT_MAX + (long long)(FORCE_MAX_ROUNDS * grid + 1) * 32 * FORCE_IPT_MAX * 2;
 }
 
 // ---- launchers (each enqueues on `s`; returns the number of kernels launched) ----
@@ -113,6 +116,8 @@ int launch_force(const GravDev &g, int phase, cudaStream_t s);
 int launch_correct(const GravDev &g, int mode, int phase, cudaStream_t s);
 int launch_snapshot_j(const GravDev &g, cudaStream_t s);  // jpos/jvel := current state (s = 0)
 int force_smem_bytes();
+int force_variant_count();
+int force_variant_info(int v, int *ctas_per_sm, int *ipt);
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
 cudaError_t force_kernel_setup();
 

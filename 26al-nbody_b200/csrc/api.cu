@@ -86,6 +86,7 @@ struct al26_ctx {
   double eps2 = 0.0, eta = 0.14, dt_max = 0.125, dt_min = 9.094947017729282e-13 /* 2^-40 */;
   int64_t n_tot = 0;
   int dbg_phase = 0;
+  int force_variant = 0;
   cudaGraphExec_t graph = nullptr;
   int graph_steps = 0;
   bool graph_stale = false;  // parameters changed since the graph captured them by value
@@ -519,7 +520,13 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   slice_of(n, c->rank, c->world, i0, nloc);
   GravDev &g = c->g;
   g.n_tot = (int)n; g.n_loc = (int)nloc; g.i0 = (int)i0;
-  g.grid_force = 2 * c->sm_count;
+  {
+    int minb = 2, ipt = 2;
+    force_variant_info(c->force_variant, &minb, &ipt);
+    g.variant = c->force_variant;
+    g.force_ipt = ipt;
+    g.grid_force = minb * c->sm_count;
+  }
   g.eps2 = c->eps2; g.eta = c->eta; g.dt_max = c->dt_max; g.dt_min = c->dt_min;
   g.part_cap = part_capacity(g.n_loc, g.grid_force);
   const size_t nl = (size_t)nloc, nt = (size_t)n;
@@ -837,7 +844,14 @@ int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const 
     if (idx[k] < 0 || idx[k] >= n) return fail(c, AL26_EINVAL, "al26_grav_force: index %d out of range", idx[k]);
   CU(cudaSetDevice(c->device));
   GravDev g{};
-  g.n_loc = g.n_tot = (int)n; g.i0 = 0; g.grid_force = 2 * c->sm_count; g.eps2 = eps2;
+  g.n_loc = g.n_tot = (int)n; g.i0 = 0; g.eps2 = eps2;
+  {
+    int minb = 2, ipt = 2;
+    force_variant_info(c->force_variant, &minb, &ipt);
+    g.variant = c->force_variant;
+    g.force_ipt = ipt;
+    g.grid_force = minb * c->sm_count;
+  }
   g.part_cap = part_capacity((int)n, g.grid_force);
   const size_t nt = (size_t)n, na = (size_t)n_act;
   double *stage = nullptr;
@@ -923,6 +937,24 @@ int al26_grav_bench_force_n(al26_ctx *c, int64_t n_act, int reps, double *avg_ms
 
 int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_per_eval) {
   return al26_grav_bench_force_n(c, 0, reps, avg_ms, pairs_per_eval);
+}
+
+int al26_set_force_variant(al26_ctx *c, int variant) {
+  if (!c) return AL26_EINVAL;
+  if (variant < 0 || variant >= force_variant_count()) return fail(c, AL26_EINVAL, "force variant %d out of range", variant);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_force_variant during evolve");
+  c->force_variant = variant;  // takes effect at the next commit (buffers and graph depend on it)
+  return 0;
+}
+
+int al26_grav_block_histogram(al26_ctx *c, int64_t *hist32) {
+  if (!c || !hist32) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "block_histogram before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  for (int b = 0; b < 32; b++) hist32[b] = c->h_hdr->nact_hist[b];
+  return 0;
 }
 
 int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {

@@ -87,16 +87,34 @@ __device__ __forceinline__ void pair_interaction(const double4 pj, const double4
   s.jz = fma(mrinv3, fma(al, dz, dvz), s.jz);
 }
 
-struct ForceSmem {
+// Kernel configuration: threads per CTA, CTAs per SM, i-particles per lane for big blocks, unroll of the
+// j loop.  Several configurations are instantiated; GravDev::variant selects one (al26_set_force_variant).
+template <int THREADS_, int MINB_, int IPT_, int UNR_>
+struct FCfg {
+  static constexpr int THREADS = THREADS_, MINB = MINB_, IPT = IPT_, UNR = UNR_, WARPS = THREADS_ / 32;
+};
+
+template <class C>
+struct ForceSmemT {
   double4 pos[FORCE_STAGES][FORCE_TJ];
   double4 vel[FORCE_STAGES][FORCE_TJ];
-  double red[FORCE_WARPS][7][64];
+  double red[C::WARPS][7][32 * C::IPT];
   unsigned long long full[FORCE_STAGES];
   int item;
 };
 
-template <int IPT>
-__device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const Decomp &d, const int n_act,
+__device__ __forceinline__ void issue_tile(const GravDev &g, double4 *spos, double4 *svel, unsigned long long *bar,
+                                           int b, int cnt) {
+  mbar_expect_tx(bar, (uint32_t)cnt * 64u);
+  tma_load_1d(spos, g.jpos + b, (uint32_t)cnt * 32u, bar);
+  tma_load_1d(svel, g.jvel + b, (uint32_t)cnt * 32u, bar);
+}
+
+// One work item.  IPT i-particles per lane.  SPLIT (IPT == 1 only, tiny blocks of n_act <= 16): the 32 lanes
+// are divided into 32/iw groups that take different j's for the same iw i-particles, and are summed with a
+// fixed xor-butterfly at the end -> the FP64 pipe time of a tiny block drops by the same factor.
+template <class C, int IPT, bool SPLIT>
+__device__ __forceinline__ void run_item(const GravDev &g, ForceSmemT<C> &sm, const Decomp &d, const int n_act,
                                          const int item, uint32_t &it) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int itile = item / d.n_jsplit, js = item - itile * d.n_jsplit;
@@ -110,19 +128,24 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const 
     for (int k = 0; k < pre; k++) {
       const int st = (it + k) % FORCE_STAGES;
       const int b = j0 + k * FORCE_TJ;
-      const int cnt = min(FORCE_TJ, j1 - b);
-      mbar_expect_tx(&sm.full[st], (uint32_t)cnt * 64u);
-      tma_load_1d(&sm.pos[st][0], g.jpos + b, (uint32_t)cnt * 32u, &sm.full[st]);
-      tma_load_1d(&sm.vel[st][0], g.jvel + b, (uint32_t)cnt * 32u, &sm.full[st]);
+      issue_tile(g, &sm.pos[st][0], &sm.vel[st][0], &sm.full[st], b, min(FORCE_TJ, j1 - b));
     }
   }
 
-  // my i-particles (identical in every warp)
+  int iw = 32;  // lanes that hold distinct i-particles
+  if (SPLIT) {
+    iw = 1;
+    while (iw < n_act) iw <<= 1;
+  }
+  const int isub = SPLIT ? (lane & (iw - 1)) : lane;
+  const int jsub = SPLIT ? (lane / iw) : 0;
+  const int jgroups = SPLIT ? (32 / iw) : 1;
+
   double xi[IPT], yi[IPT], zi[IPT], vxi[IPT], vyi[IPT], vzi[IPT];
   Acc7 s[IPT];
 #pragma unroll
   for (int q = 0; q < IPT; q++) {
-    const int slot = itile * d.ti + q * 32 + lane;
+    const int slot = itile * d.ti + q * 32 + isub;
     const int li = (slot < n_act) ? g.list[slot] : g.list[0];
     const double4 p = g.jpos[g.i0 + li];
     const double4 v = g.jvel[g.i0 + li];
@@ -131,6 +154,7 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const 
     s[q].ax = s[q].ay = s[q].az = s[q].jx = s[q].jy = s[q].jz = s[q].pot = 0.0;
   }
   const double eps2 = g.eps2;
+  const int jfirst = warp * jgroups + jsub, jstride = C::WARPS * jgroups;
 
   for (int k = 0; k < ntiles; k++, it++) {
     const int st = it % FORCE_STAGES;
@@ -139,8 +163,8 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const 
     mbar_wait(&sm.full[st], parity);
     const double4 *__restrict__ sp = sm.pos[st];
     const double4 *__restrict__ sv = sm.vel[st];
-#pragma unroll 2
-    for (int jj = warp; jj < cnt; jj += FORCE_WARPS) {
+#pragma unroll C::UNR
+    for (int jj = jfirst; jj < cnt; jj += jstride) {
       const double4 pj = sp[jj];
       const double4 vj = sv[jj];
 #pragma unroll
@@ -149,46 +173,53 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmem &sm, const 
     __syncthreads();  // every warp is done with stage st
     if (tid == 0 && k + FORCE_STAGES < ntiles) {
       const int b = j0 + (k + FORCE_STAGES) * FORCE_TJ;
-      const int c2 = min(FORCE_TJ, j1 - b);
-      mbar_expect_tx(&sm.full[st], (uint32_t)c2 * 64u);
-      tma_load_1d(&sm.pos[st][0], g.jpos + b, (uint32_t)c2 * 32u, &sm.full[st]);
-      tma_load_1d(&sm.vel[st][0], g.jvel + b, (uint32_t)c2 * 32u, &sm.full[st]);
+      issue_tile(g, &sm.pos[st][0], &sm.vel[st][0], &sm.full[st], b, min(FORCE_TJ, j1 - b));
     }
   }
 
-  // fixed-order reduction over the 8 warps
+  if (SPLIT) {  // sum the j-groups of a warp: fixed butterfly over the lane bits above log2(iw)
+    for (int o = iw; o < 32; o <<= 1) {
+      s[0].ax += __shfl_xor_sync(0xffffffffu, s[0].ax, o); s[0].ay += __shfl_xor_sync(0xffffffffu, s[0].ay, o);
+      s[0].az += __shfl_xor_sync(0xffffffffu, s[0].az, o); s[0].jx += __shfl_xor_sync(0xffffffffu, s[0].jx, o);
+      s[0].jy += __shfl_xor_sync(0xffffffffu, s[0].jy, o); s[0].jz += __shfl_xor_sync(0xffffffffu, s[0].jz, o);
+      s[0].pot += __shfl_xor_sync(0xffffffffu, s[0].pot, o);
+    }
+  }
+  // fixed-order reduction over the warps
+  if (!SPLIT || lane < iw) {
 #pragma unroll
-  for (int q = 0; q < IPT; q++) {
-    const int c = q * 32 + lane;
-    sm.red[warp][0][c] = s[q].ax; sm.red[warp][1][c] = s[q].ay; sm.red[warp][2][c] = s[q].az;
-    sm.red[warp][3][c] = s[q].jx; sm.red[warp][4][c] = s[q].jy; sm.red[warp][5][c] = s[q].jz;
-    sm.red[warp][6][c] = s[q].pot;
+    for (int q = 0; q < IPT; q++) {
+      const int c = q * 32 + lane;
+      sm.red[warp][0][c] = s[q].ax; sm.red[warp][1][c] = s[q].ay; sm.red[warp][2][c] = s[q].az;
+      sm.red[warp][3][c] = s[q].jx; sm.red[warp][4][c] = s[q].jy; sm.red[warp][5][c] = s[q].jz;
+      sm.red[warp][6][c] = s[q].pot;
+    }
   }
   __syncthreads();
-  if (tid < d.ti) {
+  if (tid < 32 * IPT && (!SPLIT || tid < iw)) {
     double r[7];
 #pragma unroll
     for (int c = 0; c < 7; c++) {
       double a = sm.red[0][c][tid];
 #pragma unroll
-      for (int w = 1; w < FORCE_WARPS; w++) a += sm.red[w][c][tid];
+      for (int w = 1; w < C::WARPS; w++) a += sm.red[w][c][tid];
       r[c] = a;
     }
     const long long o = (long long)js * d.slot_stride + (long long)itile * d.ti + tid;
     g.part_a[o] = make_double4(r[0], r[1], r[2], r[6]);
     g.part_j[o] = make_double4(r[3], r[4], r[5], 0.0);
   }
-  // red[] is next written after at least one __syncthreads of the next item's tile loop
-  // (ntiles >= 1), or after the item-fetch barrier -> no hazard.
+  // red[] is next written only after the item-fetch barrier of the next item -> no hazard.
 }
 
-__global__ void __launch_bounds__(FORCE_THREADS, 2) k_force(const GravDev g, const int phase) {
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) k_force(const GravDev g, const int phase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
+  ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
   StepCtrl *ctl = &g.ctrl[phase];
   const int n_act = ctl->n_act;
   if (n_act <= 0) return;
-  const Decomp d = make_decomp(n_act, g.n_tot, gridDim.x);
+  const Decomp d = make_decomp(n_act, g.n_tot, gridDim.x, C::IPT);
   const int n_items = d.n_itiles * d.n_jsplit;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -202,13 +233,56 @@ __global__ void __launch_bounds__(FORCE_THREADS, 2) k_force(const GravDev g, con
     __syncthreads();
     const int item = sm.item;
     if (item >= n_items) break;
-    if (d.ipt == 2) run_item<2>(g, sm, d, n_act, item, it);
-    else run_item<1>(g, sm, d, n_act, item, it);
+    if (d.ipt > 1) run_item<C, C::IPT, false>(g, sm, d, n_act, item, it);
+    else if (n_act <= FORCE_SPLIT_MAX_NACT) run_item<C, 1, true>(g, sm, d, n_act, item, it);
+    else run_item<C, 1, false>(g, sm, d, n_act, item, it);
     __syncthreads();
   }
 }
 
-int force_smem_bytes() { return (int)sizeof(ForceSmem); }
+// ---- the instantiated configurations ----
+using FV0 = FCfg<256, 2, 2, 2>;  // default
+using FV1 = FCfg<256, 2, 2, 4>;
+using FV2 = FCfg<256, 2, 2, 1>;
+using FV3 = FCfg<256, 1, 4, 1>;
+using FV4 = FCfg<256, 1, 4, 2>;
+using FV5 = FCfg<512, 1, 2, 2>;
+using FV6 = FCfg<256, 3, 1, 2>;
+using FV7 = FCfg<128, 4, 2, 2>;
+using FV8 = FCfg<256, 1, 3, 2>;
+using FV9 = FCfg<128, 3, 3, 1>;
+
+#define FOR_EACH_FORCE_VARIANT(X) X(0, FV0) X(1, FV1) X(2, FV2) X(3, FV3) X(4, FV4) X(5, FV5) X(6, FV6) X(7, FV7) X(8, FV8) X(9, FV9)
+
+int force_variant_count() { return 10; }
+
+int force_variant_info(int v, int *ctas_per_sm, int *ipt) {
+  switch (v) {
+#define X(id, cfg) case id: *ctas_per_sm = cfg::MINB; *ipt = cfg::IPT; return 0;
+    FOR_EACH_FORCE_VARIANT(X)
+#undef X
+  }
+  return -1;
+}
+
+cudaError_t force_kernel_setup() {
+  cudaError_t e = cudaSuccess;
+#define X(id, cfg) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_force<cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>));
+  FOR_EACH_FORCE_VARIANT(X)
+#undef X
+  return e;
+}
+
+int launch_force(const GravDev &g, int phase, cudaStream_t s) {
+  switch (g.variant) {
+#define X(id, cfg) case id: k_force<cfg><<<g.grid_force, cfg::THREADS, sizeof(ForceSmemT<cfg>), s>>>(g, phase); break;
+    FOR_EACH_FORCE_VARIANT(X)
+#undef X
+  }
+  return 1;
+}
+
+int force_smem_bytes() { return (int)sizeof(ForceSmemT<FV0>); }
 
 // DFMA-only microkernel: the measured FP64 roofline denominator.  8 independent
 // chains per thread, 512 threads x 2 CTAs per SM.
@@ -231,14 +305,6 @@ double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s
   return 2.0 * (double)blocks * threads * 64.0 * (double)iters;  // flops of one launch
 }
 
-cudaError_t force_kernel_setup() {
-  return cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmem));
-}
-
-int launch_force(const GravDev &g, int phase, cudaStream_t s) {
-  k_force<<<g.grid_force, FORCE_THREADS, sizeof(ForceSmem), s>>>(g, phase);
-  return 1;
-}
 
 // ------------------------------------------------------------------------------------------
 // K4: pair sums for the energies: for local i over all j,

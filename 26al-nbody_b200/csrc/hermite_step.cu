@@ -157,107 +157,151 @@ __device__ __forceinline__ double aarseth(const double eta, const double a1[3], 
   return eta * sqrt(num / den);
 }
 
-// one warp per active slot: lanes stride over the j-split partials, fixed butterfly reduction,
-// lane 0 applies the corrector.
+// corrector + ladder for one active slot, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}
+template <int MODE>
+__device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur, const int slot, const double r[7],
+                                           unsigned long long &c_bits) {
+  if (MODE == MODE_RAW) {
+    g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
+    g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
+    return;
+  }
+  const int i = g.list[slot];
+  const double a1[3] = {r[0], r[1], r[2]};
+  const double j1[3] = {r[3], r[4], r[5]};
+  if (MODE == MODE_INIT) {
+    g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
+    g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
+    const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
+    double dt0 = g.dt_max;
+    if (sa > 0.0 && sj > 0.0) dt0 = g.eta * 0.0625 * sqrt(sa / sj);
+    if (dt0 > 0.03125) dt0 = 0.03125;
+    if (dt0 > g.dt_max) dt0 = g.dt_max;
+    double dd = pow2floor(dt0);
+    if (dd < g.dt_min) dd = g.dt_min;
+    g.dt[i] = dd;
+    g.t[i] = 0.0;
+    return;
+  }
+  const double4 a0v = g.acc[i], j0v = g.jrk[i];
+  const double4 xpv = g.jpos[g.i0 + i], vpv = g.jvel[g.i0 + i];
+  const double ti = g.t[i], dti = g.dt[i];
+  const double tn = (MODE == MODE_STEP) ? bitsd(cur->t_next_bits) : g.hdr->span;
+  const double s = (MODE == MODE_STEP) ? dti : (tn - ti);
+  const double a0[3] = {a0v.x, a0v.y, a0v.z}, j0[3] = {j0v.x, j0v.y, j0v.z};
+  const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
+  double x1[3], v1[3], a2[3], a3[3];
+  const double s2 = s * s;
+  const double is2 = 1.0 / s2, is3 = 1.0 / (s2 * s);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const double da = a0[c] - a1[c];
+    const double alpha = -3.0 * da - s * (2.0 * j0[c] + j1[c]);
+    const double beta = 2.0 * da + s * (j0[c] + j1[c]);
+    x1[c] = xp[c] + s2 * (alpha * (1.0 / 12.0) + beta * (1.0 / 20.0));
+    v1[c] = vp[c] + s * (alpha * (1.0 / 3.0) + beta * 0.25);
+    a2[c] = (2.0 * alpha + 6.0 * beta) * is2;
+    a3[c] = (6.0 * beta) * is3;
+  }
+  const double m = g.pos[i].w;
+  g.pos[i] = make_double4(x1[0], x1[1], x1[2], m);
+  g.vel[i] = make_double4(v1[0], v1[1], v1[2], 0.0);
+  g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
+  g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
+  double dtA = aarseth(g.eta, a1, j1, a2, a3);
+  double nd;
+  if (MODE == MODE_STEP) {
+    nd = dti;
+    if (dtA < dti) {
+      if (0.5 * dti >= g.dt_min) nd = 0.5 * dti;
+    } else if (dtA >= 2.0 * dti && 2.0 * dti <= g.hdr->D) {
+      const double q = tn / (2.0 * dti);
+      if (q == floor(q)) nd = 2.0 * dti;
+    }
+    g.t[i] = tn;
+    g.dt[i] = nd;
+    const unsigned long long cb = dbits(tn + nd);
+    c_bits = cb < c_bits ? cb : c_bits;
+  } else {  // MODE_SYNC
+    if (dtA > g.dt_max) dtA = g.dt_max;
+    nd = pow2floor(dtA);
+    if (nd < g.dt_min) nd = g.dt_min;
+    g.t[i] = tn;
+    g.dt[i] = nd;
+  }
+}
+
+// Reduction of the j-chunk partials in a FIXED order, then the corrector.
+//   few chunks  (n_jsplit <= 32): one warp per active slot, lanes stride the chunks, xor-butterfly;
+//   many chunks (tiny blocks cut into up to `grid` chunks): one CTA per slot, all 256 threads load in
+//   parallel (one round trip instead of n_jsplit/32 dependent ones), butterfly + ordered warp sum.
 template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS) k_correct(const GravDev g, const int phase) {
   __shared__ unsigned long long sh[ST_THREADS / 32];
+  __shared__ double shr[ST_THREADS / 32][7];
   StepCtrl *cur = &g.ctrl[phase];
   StepCtrl *nxt = &g.ctrl[(phase + 1) % 3];
   const int n_act = cur->n_act;
   if (n_act <= 0) return;
-  const Decomp d = make_decomp(n_act, g.n_tot, g.grid_force);
-  const int lane = threadIdx.x & 31;
+  const Decomp d = make_decomp(n_act, g.n_tot, g.grid_force, g.force_ipt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = ST_THREADS / 32;
   unsigned long long c_bits = INF_BITS;
-  for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < n_act; slot += gridDim.x * wpb) {
-    double r[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int js = lane; js < d.n_jsplit; js += 32) {
-      const long long o = (long long)js * d.slot_stride + slot;
-      const double4 pa = g.part_a[o], pj = g.part_j[o];
-      r[0] += pa.x; r[1] += pa.y; r[2] += pa.z; r[6] += pa.w;
-      r[3] += pj.x; r[4] += pj.y; r[5] += pj.z;
-    }
-#pragma unroll
-    for (int c = 0; c < 7; c++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
-    }
-    if (lane != 0) continue;
-    if (MODE == MODE_RAW) {
-      g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
-      g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
-      continue;
-    }
-    const int i = g.list[slot];
-    const double a1[3] = {r[0], r[1], r[2]};
-    const double j1[3] = {r[3], r[4], r[5]};
-    if (MODE == MODE_INIT) {
-      g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
-      g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
-      const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
-      const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
-      double dt0 = g.dt_max;
-      if (sa > 0.0 && sj > 0.0) dt0 = g.eta * 0.0625 * sqrt(sa / sj);
-      if (dt0 > 0.03125) dt0 = 0.03125;
-      if (dt0 > g.dt_max) dt0 = g.dt_max;
-      double dd = pow2floor(dt0);
-      if (dd < g.dt_min) dd = g.dt_min;
-      g.dt[i] = dd;
-      g.t[i] = 0.0;
-      continue;
-    }
-    const double4 a0v = g.acc[i], j0v = g.jrk[i];
-    const double4 xpv = g.jpos[g.i0 + i], vpv = g.jvel[g.i0 + i];
-    const double ti = g.t[i], dti = g.dt[i];
-    const double tn = (MODE == MODE_STEP) ? bitsd(cur->t_next_bits) : g.hdr->span;
-    const double s = (MODE == MODE_STEP) ? dti : (tn - ti);
-    const double a0[3] = {a0v.x, a0v.y, a0v.z}, j0[3] = {j0v.x, j0v.y, j0v.z};
-    const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
-    double x1[3], v1[3], a2[3], a3[3];
-    const double s2 = s * s;
-    const double is2 = 1.0 / s2, is3 = 1.0 / (s2 * s);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const double da = a0[c] - a1[c];
-      const double alpha = -3.0 * da - s * (2.0 * j0[c] + j1[c]);
-      const double beta = 2.0 * da + s * (j0[c] + j1[c]);
-      x1[c] = xp[c] + s2 * (alpha * (1.0 / 12.0) + beta * (1.0 / 20.0));
-      v1[c] = vp[c] + s * (alpha * (1.0 / 3.0) + beta * 0.25);
-      a2[c] = (2.0 * alpha + 6.0 * beta) * is2;
-      a3[c] = (6.0 * beta) * is3;
-    }
-    const double m = g.pos[i].w;
-    g.pos[i] = make_double4(x1[0], x1[1], x1[2], m);
-    g.vel[i] = make_double4(v1[0], v1[1], v1[2], 0.0);
-    g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
-    g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
-    double dtA = aarseth(g.eta, a1, j1, a2, a3);
-    double nd;
-    if (MODE == MODE_STEP) {
-      nd = dti;
-      if (dtA < dti) {
-        if (0.5 * dti >= g.dt_min) nd = 0.5 * dti;
-      } else if (dtA >= 2.0 * dti && 2.0 * dti <= g.hdr->D) {
-        const double q = tn / (2.0 * dti);
-        if (q == floor(q)) nd = 2.0 * dti;
+  if (d.n_jsplit > 32) {
+    for (int slot = blockIdx.x; slot < n_act; slot += gridDim.x) {
+      double r[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int js = threadIdx.x; js < d.n_jsplit; js += ST_THREADS) {
+        const long long o = (long long)js * d.slot_stride + slot;
+        const double4 pa = g.part_a[o], pj = g.part_j[o];
+        r[0] += pa.x; r[1] += pa.y; r[2] += pa.z; r[6] += pa.w;
+        r[3] += pj.x; r[4] += pj.y; r[5] += pj.z;
       }
-      g.t[i] = tn;
-      g.dt[i] = nd;
-      const unsigned long long cb = dbits(tn + nd);
-      c_bits = cb < c_bits ? cb : c_bits;
-    } else {  // MODE_SYNC
-      if (dtA > g.dt_max) dtA = g.dt_max;
-      nd = pow2floor(dtA);
-      if (nd < g.dt_min) nd = g.dt_min;
-      g.t[i] = tn;
-      g.dt[i] = nd;
+#pragma unroll
+      for (int c = 0; c < 7; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) shr[warp][c] = r[c];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+          double a = shr[0][c];
+          for (int w = 1; w < wpb; w++) a += shr[w][c];
+          r[c] = a;
+        }
+        apply_slot<MODE>(g, cur, slot, r, c_bits);
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int slot = blockIdx.x * wpb + warp; slot < n_act; slot += gridDim.x * wpb) {
+      double r[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (lane < d.n_jsplit) {
+        const long long o = (long long)lane * d.slot_stride + slot;
+        const double4 pa = g.part_a[o], pj = g.part_j[o];
+        r[0] = pa.x; r[1] = pa.y; r[2] = pa.z; r[6] = pa.w;
+        r[3] = pj.x; r[4] = pj.y; r[5] = pj.z;
+      }
+#pragma unroll
+      for (int c = 0; c < 7; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+      }
+      if (lane == 0) apply_slot<MODE>(g, cur, slot, r, c_bits);
     }
   }
   if (MODE == MODE_STEP) block_min_to(c_bits, &nxt->t_next_bits, sh);
   if (blockIdx.x == 0 && threadIdx.x == 0 && MODE != MODE_RAW) {
     if (MODE != MODE_INIT) g.hdr->n_steps += 1;
     g.hdr->n_pairs += (long long)n_act * (long long)g.n_tot;
+    int b = 0;
+    while ((1 << (b + 1)) <= n_act && b < 31) b++;
+    g.hdr->nact_hist[b] += 1;  // diagnostic: log2 histogram of the block sizes
   }
 }
 

@@ -118,6 +118,11 @@ int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pair
 /* same with only the first n_act (<= 0: all) local particles active: the small-block regime */
 int al26_grav_bench_force_n(al26_ctx *ctx, int64_t n_act, int reps, double *avg_ms, int64_t *pairs_per_eval);
 
+/* tuning hook: pick one of the compiled force-kernel configurations (0 = default); applies at the
+ * next al26_grav_commit */
+int al26_set_force_variant(al26_ctx *ctx, int variant);
+/* diagnostic: number of block steps by floor(log2(n_active)) since the last commit (32 bins) */
+int al26_grav_block_histogram(al26_ctx *ctx, int64_t *hist32);
 /* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
  * the roofline denominator of the force kernel */
 int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);

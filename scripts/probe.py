@@ -6,6 +6,19 @@ pkg = importlib.import_module("26al-nbody_b200")
 ctx = pkg.Context(0)
 print("device", ctx.device_info())
 print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+if os.environ.get("PROBE_VARIANTS"):
+    n = 100000
+    c = pkg.ic.cluster(n, seed=0)
+    for v in range(10):
+        ctx.set_force_variant(v)
+        g = pkg.GravityCore(ctx=ctx)
+        g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+        row = []
+        for na, reps in ((0, 3), (20000, 5), (5000, 10), (1000, 20), (300, 20), (32, 20), (8, 20), (1, 20)):
+            ms, pairs = g.bench_force(reps, n_act=na)
+            row.append(f"{na or n}:{ms*1e3:.1f}us/{pairs/ms*1e-6:.0f}G")
+        print(f"variant {v}: " + "  ".join(row), flush=True)
+    ctx.set_force_variant(0)
 for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
     c = pkg.ic.cluster(n, seed=0)
     g = pkg.GravityCore(ctx=ctx)
@@ -33,5 +46,6 @@ for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
         print(f"  span 2^{lg}: {steps} block steps, {pairs:.3e} pairs, dev {ms:.2f} ms, wall {wall*1e3:.2f} ms, "
               f"{pairs/ms*1e-6:.1f} Gpairs/s, {ms*1e3/max(steps,1):.1f} us/step, mean n_act {pairs/n/max(steps,1):.0f}, launches {nl}")
         if wall > 60: break
+    print("  block-size histogram (log2 bins):", {b: h for b, h in enumerate(ctx.block_histogram()) if h})
     k1, u1, _ = g.energies()
     print("  dE/E", ((k0 + u0) - (k1 + u1)) / (k1 + u1), "t=", tnow)

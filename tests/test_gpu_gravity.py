@@ -63,6 +63,24 @@ def test_force_subset_ragged_and_coincident(pkg, grav):
     assert vec_rel(out[:3], ref[:3]) < TOL and vec_rel(out[3:6], ref[3:6]) < TOL
 
 
+@pytest.mark.parametrize("variant", range(10))
+def test_force_variants_parity(pkg, ctx, variant):
+    """every compiled force-kernel configuration, big blocks, ragged blocks and tiny (lane-split) blocks"""
+    ctx.set_force_variant(variant)
+    try:
+        g = pkg.GravityCore(ctx=ctx)
+        p = make(pkg, 6000, seed=variant)
+        rng = np.random.default_rng(variant)
+        for k in (6000, 4500, 100, 16, 9, 5, 2, 1):
+            idx = np.sort(rng.choice(6000, k, replace=False)).astype(np.int32)
+            out = g.force(*p, idx=idx)
+            ref = H.force(*p, idx=idx, long_double=True)
+            assert vec_rel(out[:3], ref[:3]) < TOL and vec_rel(out[3:6], ref[3:6]) < TOL, (variant, k)
+            assert np.max(np.abs(out[6] - ref[6]) / np.abs(ref[6])) < TOL
+    finally:
+        ctx.set_force_variant(0)
+
+
 def test_force_is_deterministic(pkg, grav):
     p = make(pkg, 2500, seed=9)
     a = grav.force(*p)
