@@ -184,6 +184,7 @@ class _GravityParticles:
         pos = [cv.length_to_nbody(getattr(cluster, a)) for a in ("x", "y", "z")]
         vel = [cv.speed_to_nbody(getattr(cluster, a)) for a in ("vx", "vy", "vz")]
         o._core.commit(m, *pos, *vel)
+        o._mtot = float(np.sum(m))
         self.key = np.array(cluster.key, dtype=np.uint64, copy=True)
         self.radius = getattr(cluster, "radius", None)
         o._cache = None
@@ -211,7 +212,9 @@ class _GravityParticles:
     def __setattr__(self, name, value):
         if name == "mass":
             o = self._o
-            o._core.set_mass(o.converter.mass_to_nbody(value))
+            m = o.converter.mass_to_nbody(value)
+            o._core.set_mass(m)
+            o._mtot = float(np.sum(m))
             o._cache = None
             return
         object.__setattr__(self, name, value)
@@ -289,8 +292,7 @@ class B200Gravity:
     def virial_radius(self):
         """`cluster.virial_radius()` (al26_nbody.py:770) from the same pair reduction."""
         _, _, s = self._core.energies()
-        mtot = float(np.sum(self._core.get_state()[0]))
-        return self.converter.length_to_si(mtot * mtot / (2.0 * s))
+        return self.converter.length_to_si(self._mtot * self._mtot / (2.0 * s))
 
     def stop(self):
         self._core.close()
