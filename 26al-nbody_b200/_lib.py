@@ -62,7 +62,9 @@ SIGNATURES = {
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
     "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),
+    "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
+    "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
@@ -147,10 +149,18 @@ class Context:
     def set_force_variant(self, v):
         self.chk(self.L.al26_set_force_variant(self.h, int(v)))
 
+    def set_step_mode(self, mode):
+        self.chk(self.L.al26_set_step_mode(self.h, int(mode)))
+
     def block_histogram(self):
         h = (C.c_int64 * 32)()
         self.chk(self.L.al26_grav_block_histogram(self.h, h))
         return list(h)
+
+    def loop_profile(self):
+        h = (C.c_int64 * 6)()
+        self.chk(self.L.al26_grav_loop_profile(self.h, h))
+        return dict(zip(("predict", "bar1", "force", "bar2", "correct", "bar3"), list(h)))
 
     def fp64_peak_tflops(self):
         tf = C.c_double(0)

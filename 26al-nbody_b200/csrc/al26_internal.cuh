@@ -31,6 +31,11 @@ struct GravHeader {
   long long n_steps;  // block steps taken (this rank)
   long long n_pairs;  // (i,j) pair evaluations (this rank)
   long long nact_hist[32];  // diagnostic: block steps by floor(log2(n_act)), since the last commit
+  unsigned int bar_counter;  // grid barrier of the persistent loop kernel (zeroed before every launch)
+  int loop_error;            // raised when a barrier spin limit is hit
+  int phase;                 // StepCtrl phase after the last loop-kernel launch
+  int pad2;
+  long long loop_cycles[6];  // diagnostic: CTA 0's SM cycles in predict / barrier / force / barrier / correct / barrier
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
@@ -42,6 +47,7 @@ struct GravDev {
   int grid_force;
   int variant;    // force-kernel configuration (hermite_force.cu)
   int force_ipt;  // its i-particles per lane for big blocks
+  const int *decomp_tab;  // n_jsplit by number of i-tiles (fill_decomp_table)
   double eps2, eta, dt_max, dt_min;
   double4 *pos, *vel, *acc, *jrk;
   double *t, *dt;
@@ -59,9 +65,9 @@ struct GravDev {
 // the force kernel and the reduce/corrector kernel agree without communicating ----
 constexpr int FORCE_TJ = 256;      // j per TMA tile (2 x 8 KB per stage)
 constexpr int FORCE_STAGES = 3;
-constexpr int FORCE_MIN_JCHUNK = 256;
+constexpr int FORCE_MIN_JCHUNK = 64;
 constexpr int FORCE_MAX_ROUNDS = 16;             // work items per CTA at most (load balance for big blocks)
-constexpr long long FORCE_ITEM_PAIRS = 250000;   // do not cut items finer than this many pairs (~150 us)
+constexpr double FORCE_ITEM_OVERHEAD_PAIRS = 3200.0;  // fixed cost of one item (TMA prologue, barriers, reduction) in pair units
 constexpr int FORCE_BIG_NACT_PER_IPT = 1024;      // n_act >= this x IPT: IPT i-particles per lane
 constexpr int FORCE_SPLIT_MAX_NACT = 16;         // n_act <= this: lanes split over j as well (tiny blocks)
 constexpr int FORCE_IPT_MAX = 4;
@@ -75,25 +81,54 @@ struct Decomp {
   int slot_stride;  // n_itiles * ti
 };
 
-// Items = n_itiles x n_jsplit, handed out dynamically.  Small blocks: one round, at most `grid` items
-// (every CTA gets one big item; per-item overhead -- TMA prologue, barrier, reduction -- is paid once).
-// Big blocks: up to FORCE_MAX_ROUNDS rounds so the tail of the last round stays small.  The item
-// count is kept just BELOW a multiple of the grid so the last round is full.
-__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, int grid, int ipt_big) {
+// Items = n_itiles x n_jsplit, handed out dynamically.  n_jsplit is chosen among the candidates
+// floor(k * grid / n_itiles), k = 1..FORCE_MAX_ROUNDS (item count just below a multiple of the grid, so the
+// last round is full) to maximise  (fill of the last round) x (item work / (item work + fixed item cost)):
+// small blocks get one round of big items, big blocks get many rounds so the tail stays short.
+// The search runs on the HOST once per commit (decomp_table); kernels only look the answer up.
+inline int choose_jsplit(int n_itiles, int ti, int n_tot, int grid) {
+  int max_by_j = n_tot / FORCE_MIN_JCHUNK;
+  if (max_by_j < 1) max_by_j = 1;
+  int best_ns = 1, prev = 0;
+  double best_eff = -1.0;
+  for (int k = 1; k <= FORCE_MAX_ROUNDS; k++) {
+    int ns = (int)(((long long)k * grid) / n_itiles);
+    if (ns > max_by_j) ns = max_by_j;
+    if (ns < 1) ns = 1;
+    if (ns == prev) continue;
+    prev = ns;
+    const long long items = (long long)n_itiles * ns;
+    const long long rounds = (items + grid - 1) / grid;
+    const double w = (double)ti * (double)((n_tot + ns - 1) / ns);
+    const double eff = ((double)items / (double)(rounds * grid)) * (w / (w + FORCE_ITEM_OVERHEAD_PAIRS));
+    if (eff > best_eff) {
+      best_eff = eff;
+      best_ns = ns;
+    }
+  }
+  return best_ns;
+}
+
+// table layout: entries [0, n_small) for ipt = 1 (index n_itiles - 1), then entries for ipt = ipt_big
+inline int decomp_small_entries(int ipt_big) { return (FORCE_BIG_NACT_PER_IPT * ipt_big + 31) / 32 + 1; }
+inline int decomp_table_entries(int n_loc, int ipt_big) {
+  return decomp_small_entries(ipt_big) + (n_loc + 32 * ipt_big - 1) / (32 * ipt_big) + 2;
+}
+inline void fill_decomp_table(int *tab, int n_loc, int n_tot, int grid, int ipt_big) {
+  const int ns_small = decomp_small_entries(ipt_big);
+  for (int t = 1; t <= ns_small; t++) tab[t - 1] = choose_jsplit(t, 32, n_tot, grid);
+  const int nb = decomp_table_entries(n_loc, ipt_big) - ns_small;
+  for (int t = 1; t <= nb; t++) tab[ns_small + t - 1] = choose_jsplit(t, 32 * ipt_big, n_tot, grid);
+}
+
+__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, const int *__restrict__ tab, int ipt_big) {
   Decomp d;
   d.ipt = (n_act >= FORCE_BIG_NACT_PER_IPT * ipt_big) ? ipt_big : 1;
   d.ti = 32 * d.ipt;
   d.n_itiles = (n_act + d.ti - 1) / d.ti;
   if (d.n_itiles < 1) d.n_itiles = 1;
-  const long long total = (long long)d.n_itiles * d.ti * (long long)n_tot;
-  long long rounds = total / ((long long)grid * FORCE_ITEM_PAIRS);
-  if (rounds < 1) rounds = 1;
-  if (rounds > FORCE_MAX_ROUNDS) rounds = FORCE_MAX_ROUNDS;
-  int ns = (int)((rounds * grid) / d.n_itiles);
-  int max_by_j = n_tot / FORCE_MIN_JCHUNK;
-  if (max_by_j < 1) max_by_j = 1;
-  if (ns > max_by_j) ns = max_by_j;
-  if (ns < 1) ns = 1;
+  const int small = (FORCE_BIG_NACT_PER_IPT * ipt_big + 31) / 32 + 1;
+  const int ns = tab[(d.ipt == 1 ? 0 : small) + d.n_itiles - 1];
   int jc = (n_tot + ns - 1) / ns;
   jc = (jc + 7) & ~7;
   if (jc < 8) jc = 8;
@@ -120,6 +155,9 @@ int force_variant_count();
 int force_variant_info(int v, int *ctas_per_sm, int *ipt);
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
 cudaError_t force_kernel_setup();
+int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cudaError_t *err);
+cudaError_t loop_kernel_setup();
+int loop_max_ctas_per_sm(int variant);
 
 // energies (K4): per-rank partial sums over local i x all j
 struct EnergyDev {

@@ -87,6 +87,8 @@ struct al26_ctx {
   int64_t n_tot = 0;
   int dbg_phase = 0;
   int force_variant = 0;
+  int step_mode = 1;      // 1: persistent cooperative loop kernel (1 GPU), 0: CUDA graph of 3 kernels per block step
+  bool coop_ok = false;   // device supports cooperative launch
   cudaGraphExec_t graph = nullptr;
   int graph_steps = 0;
   bool graph_stale = false;  // parameters changed since the graph captured them by value
@@ -187,6 +189,10 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
   }
 }
 __global__ void k_reset_work(StepCtrl *ctrl) { ctrl->work_counter = 0; }
+__global__ void k_loop_prepare(GravHeader *hdr) {
+  hdr->bar_counter = 0u;
+  hdr->loop_error = 0;
+}
 __global__ void k_set_nact(StepCtrl *ctrl, int n_act) {
   ctrl->n_act = n_act;
   ctrl->work_counter = 0;
@@ -231,7 +237,8 @@ void free_gravity(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   c->graph = nullptr;
   GravDev &g = c->g;
-  void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr};
+  void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr,
+                  (void *)g.decomp_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   g = GravDev{};
@@ -338,6 +345,26 @@ int read_header(al26_ctx *c) {
   return 0;
 }
 
+bool use_loop(al26_ctx *c) {
+  if (c->step_mode != 1 || c->world != 1 || !c->coop_ok) return false;
+  int minb = 2, ipt = 2;
+  force_variant_info(c->force_variant, &minb, &ipt);
+  return loop_max_ctas_per_sm(c->force_variant) >= minb;
+}
+
+// up to max_steps block steps inside one cooperative launch; refreshes the host copy of the header
+int run_loop(al26_ctx *c, int max_steps) {
+  k_loop_prepare<<<1, 1, 0, c->stream>>>(c->g.hdr);
+  cudaError_t e = cudaSuccess;
+  c->launches += 1 + launch_loop(c->g, c->dbg_phase, max_steps, c->stream, &e);
+  if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the loop kernel failed: %s", cudaGetErrorString(e));
+  int rc = read_header(c);
+  if (rc) return rc;
+  if (c->h_hdr->loop_error) return fail(c, AL26_ECUDA, "loop kernel: grid barrier spin limit hit");
+  c->dbg_phase = c->h_hdr->phase;
+  return 0;
+}
+
 int begin_evolve(al26_ctx *c, double t_end) {
   if (!c->committed) return fail(c, AL26_ESTATE, "evolve before commit");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "evolve already in progress");
@@ -416,12 +443,16 @@ al26_ctx *al26_create(int device_id) {
             cudaMallocHost(&c->h_hdr, sizeof(GravHeader)) == cudaSuccess &&
             cudaMallocHost(&c->h_small, 16 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&c->h_events, (8 + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
-            cudaMalloc(&c->en_out, 4 * sizeof(double)) == cudaSuccess && force_kernel_setup() == cudaSuccess;
+            cudaMalloc(&c->en_out, 4 * sizeof(double)) == cudaSuccess && force_kernel_setup() == cudaSuccess &&
+            loop_kernel_setup() == cudaSuccess;
   if (!ok) {
     fail(nullptr, AL26_ECUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
     return nullptr;
   }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_id);
+  c->coop_ok = coop != 0;
   return c;
 }
 
@@ -543,6 +574,14 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   CU(cudaMalloc(&g.part_j, (size_t)g.part_cap * sizeof(double4)));
   CU(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
   CU(cudaMalloc(&g.hdr, sizeof(GravHeader)));
+  {
+    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt));
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt);
+    int *d_tab = nullptr;
+    CU(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
+    CU(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    g.decomp_tab = d_tab;
+  }
   CU(cudaMemsetAsync(g.acc, 0, nl * sizeof(double4), c->stream));
   CU(cudaMemsetAsync(g.jrk, 0, nl * sizeof(double4), c->stream));
   CU(cudaMemsetAsync(g.t, 0, nl * sizeof(double), c->stream));
@@ -621,19 +660,26 @@ int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t 
   CU(cudaEventRecord(c->ev0, c->stream));
   int rc = begin_evolve(c, t_end);
   if (rc) return rc;
-  int launches_needed = 0;
-  int batch = c->expected_graph_launches > 1 ? c->expected_graph_launches - 1 : 1;
-  while (true) {
-    for (int b = 0; b < batch; b++) {
-      CU(cudaGraphLaunch(c->graph, c->stream));
-      c->launches += 3 * c->graph_steps;
-      launches_needed++;
+  if (use_loop(c)) {
+    while (true) {
+      if ((rc = run_loop(c, 1 << 30))) { c->in_evolve = false; return rc; }
+      if (c->h_hdr->done) break;
     }
-    batch = 1;
-    if ((rc = read_header(c))) { c->in_evolve = false; return rc; }
-    if (c->h_hdr->done) break;
+  } else {
+    int launches_needed = 0;
+    int batch = c->expected_graph_launches > 1 ? c->expected_graph_launches - 1 : 1;
+    while (true) {
+      for (int b = 0; b < batch; b++) {
+        CU(cudaGraphLaunch(c->graph, c->stream));
+        c->launches += 3 * c->graph_steps;
+        launches_needed++;
+      }
+      batch = 1;
+      if ((rc = read_header(c))) { c->in_evolve = false; return rc; }
+      if (c->h_hdr->done) break;
+    }
+    c->expected_graph_launches = launches_needed;
   }
-  c->expected_graph_launches = launches_needed;
   rc = finish_evolve(c);
   if (rc) { c->in_evolve = false; return rc; }
   CU(cudaEventRecord(c->ev1, c->stream));
@@ -666,6 +712,15 @@ int al26_grav_dbg_advance(al26_ctx *c, int64_t max_steps, int64_t *n_done, int *
     int rc = read_header(c);
     if (rc) return rc;
     const long long before = c->h_hdr->n_steps;
+    if (use_loop(c)) {
+      if ((rc = run_loop(c, 1))) return rc;
+      if (c->h_hdr->done) {
+        fin = 1;
+        break;
+      }
+      done += c->h_hdr->n_steps - before;
+      continue;
+    }
     if ((rc = enqueue_step(c, MODE_STEP, c->dbg_phase))) return rc;
     if ((rc = read_header(c))) return rc;
     if (c->h_hdr->done) {
@@ -870,6 +925,14 @@ int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const 
   TRY(cudaMalloc(&g.raw_j, na * sizeof(double4)));
   TRY(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
   TRY(cudaMalloc(&g.hdr, sizeof(GravHeader)));
+  int *d_tab = nullptr;
+  {
+    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt));
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt);
+    TRY(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
+    TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    g.decomp_tab = d_tab;
+  }
   const double *src[7] = {m, x, y, z, vx, vy, vz};
   for (int k = 0; k < 7; k++) TRY(cudaMemcpyAsync(stage + k * nt, src[k], nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   TRY(cudaMemcpyAsync(d_idx, idx, na * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -890,7 +953,7 @@ int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const 
   }
 #undef TRY
   if (e != cudaSuccess) rc = fail(c, AL26_ECUDA, "al26_grav_force: %s", cudaGetErrorString(e));
-  void *ptrs[] = {stage, g.jpos, g.jvel, g.list, d_idx, g.part_a, g.part_j, g.raw_a, g.raw_j, g.ctrl, g.hdr};
+  void *ptrs[] = {stage, g.jpos, g.jvel, g.list, d_idx, g.part_a, g.part_j, g.raw_a, g.raw_j, g.ctrl, g.hdr, d_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   return rc;
@@ -947,6 +1010,14 @@ int al26_set_force_variant(al26_ctx *c, int variant) {
   return 0;
 }
 
+int al26_set_step_mode(al26_ctx *c, int mode) {
+  if (!c) return AL26_EINVAL;
+  if (mode != 0 && mode != 1) return fail(c, AL26_EINVAL, "step mode must be 0 (graph) or 1 (persistent loop)");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_step_mode during evolve");
+  c->step_mode = mode;
+  return 0;
+}
+
 int al26_grav_block_histogram(al26_ctx *c, int64_t *hist32) {
   if (!c || !hist32) return AL26_EINVAL;
   if (!c->committed) return fail(c, AL26_ESTATE, "block_histogram before commit");
@@ -954,6 +1025,16 @@ int al26_grav_block_histogram(al26_ctx *c, int64_t *hist32) {
   int rc = read_header(c);
   if (rc) return rc;
   for (int b = 0; b < 32; b++) hist32[b] = c->h_hdr->nact_hist[b];
+  return 0;
+}
+
+int al26_grav_loop_profile(al26_ctx *c, int64_t *cycles6) {
+  if (!c || !cycles6) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "loop_profile before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  for (int k = 0; k < 6; k++) cycles6[k] = c->h_hdr->loop_cycles[k];
   return 0;
 }
 

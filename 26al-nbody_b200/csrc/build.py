@@ -2,8 +2,7 @@
 
     python 26al-nbody_b200/csrc/build.py [--force] [--verbose]
 
-hermite_step.cu and enrich.cu are compiled with --fmad=false: their arithmetic has to follow
-the reference's / the oracle's evaluation order bit for bit (see the file headers).
+Every unit is compiled with --fmad=false (see UNITS below).
 """
 import os
 import subprocess
@@ -13,13 +12,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libal26b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"] + ARCH
+# --fmad=false everywhere: the corrector / ladder / enrichment arithmetic has to follow the oracle's and the
+# reference's evaluation order bit for bit; the force kernel writes every FMA explicitly (fma()), so the
+# flag does not change its SASS.
 UNITS = [
-    ("hermite_force.cu", []),
+    ("hermite_force.cu", ["--fmad=false"]),
     ("hermite_step.cu", ["--fmad=false"]),
+    ("hermite_loop.cu", ["--fmad=false"]),
     ("enrich.cu", ["--fmad=false"]),
-    ("api.cu", []),
+    ("api.cu", ["--fmad=false"]),
 ]
-DEPS = ["al26_internal.cuh", os.path.join("..", "..", "include", "al26_b200.h")]
+DEPS = ["al26_internal.cuh", "hermite_force.cuh", "hermite_step.cuh", os.path.join("..", "..", "include", "al26_b200.h")]
 
 
 def _newer(target, sources):

@@ -1,0 +1,265 @@
+// hermite_step.cuh -- device-side pieces of the block-timestep machinery, shared by the stand-alone
+// kernels (hermite_step.cu) and the persistent loop kernel (hermite_loop.cu).  Every translation unit
+// of the library is compiled with --fmad=false: the arithmetic below follows the CPU oracle's
+// evaluation order, so given identical inputs every timestep / scheduling decision is bit-identical.
+//   phase_predict_list  predictor for every local j fused with the scheduler (row G5):
+//                       ballot compaction of THIS step's active list, warp-shuffle + one atomicMin per
+//                       block of min(t+dt) over the non-active particles for the NEXT step
+//   phase_correct       fixed-order reduction of the force partials, Hermite corrector, Aarseth criterion
+//                       and the dyadic ladder (row G4); folds the active particles' new t+dt into the
+//                       same minimum
+// Stand-ins for ph4's jdata::predict_all, idata::correct and scheduler behind gravity.evolve_model
+// (al26_nbody.py:833).
+#pragma once
+#include "al26_internal.cuh"
+
+namespace al26 {
+
+constexpr int ST_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+__device__ __forceinline__ double bitsd(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+__device__ __forceinline__ double pow2floor(double x) {  // x > 0, normal
+  return __longlong_as_double(__double_as_longlong(x) & 0x7FF0000000000000ll);
+}
+
+// L2 (cache-global) load of a double4: bypasses the non-coherent L1
+__device__ __forceinline__ double4 ldcg_d4(const double4 *p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+// block-wide min -> one atomicMin per block.  sh: >= blockDim.x/32 entries of shared memory.
+__device__ __forceinline__ void block_min_to(unsigned long long v, unsigned long long *dst, unsigned long long *sh) {
+  v = warp_min_u64(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : INF_BITS;
+    w = warp_min_u64(w);
+    if (lane == 0 && w != INF_BITS) atomicMin(dst, w);
+  }
+}
+
+// Predict every local particle to `tn` into the global j-set, build the active list of this step in
+// cur->n_act / g.list, and fold min(t+dt) of the non-active particles into nxt->t_next_bits.
+// (block_id, n_blocks) describe the caller's grid; every block runs the same number of iterations.
+template <int MODE>
+__device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
+                                                   const int block_id, const int n_blocks, unsigned long long *sh) {
+  const int nthr = blockDim.x;
+  unsigned long long c_min = INF_BITS;
+  for (int base = block_id * nthr; base < g.n_loc; base += n_blocks * nthr) {
+    const int i = base + threadIdx.x;
+    bool active = false;
+    if (i < g.n_loc) {
+      const double4 p = g.pos[i], v = g.vel[i], a = g.acc[i], j = g.jrk[i];
+      const double ti = g.t[i], dti = g.dt[i];
+      const double s = (MODE == MODE_INIT) ? 0.0 : (tn - ti);  // init: predicted == current, whatever t holds
+      const double s2 = s * s * 0.5, s3 = s * s * s * (1.0 / 6.0);
+      double4 pp, pv;
+      pp.x = p.x + v.x * s + a.x * s2 + j.x * s3;
+      pp.y = p.y + v.y * s + a.y * s2 + j.y * s3;
+      pp.z = p.z + v.z * s + a.z * s2 + j.z * s3;
+      pp.w = p.w;
+      pv.x = v.x + a.x * s + j.x * s2;
+      pv.y = v.y + a.y * s + j.y * s2;
+      pv.z = v.z + a.z * s + j.z * s2;
+      pv.w = 0.0;
+      g.jpos[g.i0 + i] = pp;
+      g.jvel[g.i0 + i] = pv;
+      const double c = ti + dti;
+      if (MODE == MODE_STEP) active = (c == tn);
+      else if (MODE == MODE_INIT) active = true;
+      else active = (ti < tn);
+      if (!active) {
+        const unsigned long long cb = dbits(c);
+        c_min = cb < c_min ? cb : c_min;
+      }
+    }
+    // ballot compaction (order within the list is irrelevant to the results: every slot's force sum
+    // runs over j in a fixed order)
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int b0 = 0;
+      if (lane == (__ffs(m) - 1)) b0 = atomicAdd(&cur->n_act, __popc(m));
+      b0 = __shfl_sync(0xffffffffu, b0, __ffs(m) - 1);
+      if (active) g.list[b0 + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+  }
+  if (MODE == MODE_STEP) block_min_to(c_min, &nxt->t_next_bits, sh);
+}
+
+// Aarseth estimate; mirrors oracle/hermite_oracle.c: aarseth()
+__device__ __forceinline__ double aarseth(const double eta, const double a1[3], const double j1[3],
+                                          const double a2[3], const double a3[3]) {
+  const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+  const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
+  const double s2 = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2];
+  const double s3 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
+  const double num = sqrt(sa * s2) + sj;
+  const double den = sqrt(sj * s3) + s2;
+  if (!(den > 0.0) || !(num > 0.0)) return 1.0e300;
+  return eta * sqrt(num / den);
+}
+
+// corrector + ladder for one active slot, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}
+template <int MODE>
+__device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur, const int slot, const double r[7],
+                                           unsigned long long &c_bits) {
+  if (MODE == MODE_RAW) {
+    g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
+    g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
+    return;
+  }
+  const int i = g.list[slot];
+  const double a1[3] = {r[0], r[1], r[2]};
+  const double j1[3] = {r[3], r[4], r[5]};
+  if (MODE == MODE_INIT) {
+    g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
+    g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
+    const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
+    double dt0 = g.dt_max;
+    if (sa > 0.0 && sj > 0.0) dt0 = g.eta * 0.0625 * sqrt(sa / sj);
+    if (dt0 > 0.03125) dt0 = 0.03125;
+    if (dt0 > g.dt_max) dt0 = g.dt_max;
+    double dd = pow2floor(dt0);
+    if (dd < g.dt_min) dd = g.dt_min;
+    g.dt[i] = dd;
+    g.t[i] = 0.0;
+    return;
+  }
+  const double4 a0v = g.acc[i], j0v = g.jrk[i];
+  const double4 xpv = g.jpos[g.i0 + i], vpv = g.jvel[g.i0 + i];
+  const double ti = g.t[i], dti = g.dt[i];
+  const double tn = (MODE == MODE_STEP) ? bitsd(cur->t_next_bits) : g.hdr->span;
+  const double s = (MODE == MODE_STEP) ? dti : (tn - ti);
+  const double a0[3] = {a0v.x, a0v.y, a0v.z}, j0[3] = {j0v.x, j0v.y, j0v.z};
+  const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
+  double x1[3], v1[3], a2[3], a3[3];
+  const double s2 = s * s;
+  const double is2 = 1.0 / s2, is3 = 1.0 / (s2 * s);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const double da = a0[c] - a1[c];
+    const double alpha = -3.0 * da - s * (2.0 * j0[c] + j1[c]);
+    const double beta = 2.0 * da + s * (j0[c] + j1[c]);
+    x1[c] = xp[c] + s2 * (alpha * (1.0 / 12.0) + beta * (1.0 / 20.0));
+    v1[c] = vp[c] + s * (alpha * (1.0 / 3.0) + beta * 0.25);
+    a2[c] = (2.0 * alpha + 6.0 * beta) * is2;
+    a3[c] = (6.0 * beta) * is3;
+  }
+  const double m = g.pos[i].w;
+  g.pos[i] = make_double4(x1[0], x1[1], x1[2], m);
+  g.vel[i] = make_double4(v1[0], v1[1], v1[2], 0.0);
+  g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
+  g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
+  double dtA = aarseth(g.eta, a1, j1, a2, a3);
+  double nd;
+  if (MODE == MODE_STEP) {
+    nd = dti;
+    if (dtA < dti) {
+      if (0.5 * dti >= g.dt_min) nd = 0.5 * dti;
+    } else if (dtA >= 2.0 * dti && 2.0 * dti <= g.hdr->D) {
+      const double q = tn / (2.0 * dti);
+      if (q == floor(q)) nd = 2.0 * dti;
+    }
+    g.t[i] = tn;
+    g.dt[i] = nd;
+    const unsigned long long cb = dbits(tn + nd);
+    c_bits = cb < c_bits ? cb : c_bits;
+  } else {  // MODE_SYNC
+    if (dtA > g.dt_max) dtA = g.dt_max;
+    nd = pow2floor(dtA);
+    if (nd < g.dt_min) nd = g.dt_min;
+    g.t[i] = tn;
+    g.dt[i] = nd;
+  }
+}
+
+// Reduction of the j-chunk partials in a FIXED order, then the corrector.
+//   few chunks  (n_jsplit <= 32): one warp per active slot, lanes take one chunk each, xor-butterfly;
+//   many chunks (tiny blocks cut into up to `grid` chunks): one CTA per slot, all threads load in
+//   parallel (one round trip instead of n_jsplit/32 dependent ones), butterfly + ordered warp sum.
+// sh: blockDim/32 u64, shr: blockDim/32 x 7 doubles of shared memory.
+template <int MODE>
+__device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const int n_act,
+                                              const int block_id, const int n_blocks, unsigned long long *sh,
+                                              double (*shr)[7]) {
+  const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  unsigned long long c_bits = INF_BITS;
+  if (d.n_jsplit > 32) {
+    for (int slot = block_id; slot < n_act; slot += n_blocks) {
+      double r[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int js = threadIdx.x; js < d.n_jsplit; js += blockDim.x) {
+        const long long o = (long long)js * d.slot_stride + slot;
+        const double4 pa = ldcg_d4(&g.part_a[o]), pj = ldcg_d4(&g.part_j[o]);
+        r[0] += pa.x; r[1] += pa.y; r[2] += pa.z; r[6] += pa.w;
+        r[3] += pj.x; r[4] += pj.y; r[5] += pj.z;
+      }
+#pragma unroll
+      for (int c = 0; c < 7; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+      }
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) shr[warp][c] = r[c];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+          double a = shr[0][c];
+          for (int w = 1; w < wpb; w++) a += shr[w][c];
+          r[c] = a;
+        }
+        apply_slot<MODE>(g, cur, slot, r, c_bits);
+      }
+    }
+  } else {
+    for (int slot = block_id * wpb + warp; slot < n_act; slot += n_blocks * wpb) {
+      double r[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (lane < d.n_jsplit) {
+        const long long o = (long long)lane * d.slot_stride + slot;
+        const double4 pa = ldcg_d4(&g.part_a[o]), pj = ldcg_d4(&g.part_j[o]);
+        r[0] = pa.x; r[1] = pa.y; r[2] = pa.z; r[6] = pa.w;
+        r[3] = pj.x; r[4] = pj.y; r[5] = pj.z;
+      }
+#pragma unroll
+      for (int c = 0; c < 7; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+      }
+      if (lane == 0) apply_slot<MODE>(g, cur, slot, r, c_bits);
+    }
+  }
+  if (MODE == MODE_STEP) block_min_to(c_bits, &nxt->t_next_bits, sh);
+  if (block_id == 0 && threadIdx.x == 0 && MODE != MODE_RAW) {
+    if (MODE != MODE_INIT) g.hdr->n_steps += 1;
+    g.hdr->n_pairs += (long long)n_act * (long long)g.n_tot;
+    int b = 0;
+    while ((1 << (b + 1)) <= n_act && b < 31) b++;
+    g.hdr->nact_hist[b] += 1;  // diagnostic: log2 histogram of the block sizes
+  }
+}
+
+}  // namespace al26

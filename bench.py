@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-enrich", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (scaling sweeps at N=1e6)")
+    ap.add_argument("--step-mode", type=int, default=1, choices=[0, 1], help="1 GPU: 1 = persistent loop kernel, 0 = CUDA graph")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     return ap.parse_args()
 
@@ -236,6 +238,7 @@ def main():
     torch.cuda.set_device(local)
     pkg = importlib.import_module("26al-nbody_b200")
     ctx = pkg.Context(local)
+    ctx.set_step_mode(args.step_mode)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pkg.dist.init_context(ctx, rank, world, device="cuda")
@@ -320,22 +323,25 @@ def main():
         g.get_state(outs_np)             # grav_to_clus.copy() / bulk getters        (:876,886-891)
         return s_, p_, g.last_device_ms()[1]
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    e_pairs = 0.0
     e_launch = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        s_, p_, nl = e2e_step()
-        e_pairs += p_
-        e_launch += nl
-    barrier()
-    e_wall = allmax(time.perf_counter() - t0)
-    e_pairs = allsum(float(e_pairs))
-    e2e = {"value": e_pairs / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 7 * 8 * n,
-           "ms_per_step": 1e3 * e_wall / args.steps,
-           "note": "set_mass (dirty -> full re-initialisation, as the reference's per-step mass channel forces) + evolve + get_state"}
+    if args.no_e2e:
+        e2e = None
+    else:
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        e_pairs = 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_, p_, nl = e2e_step()
+            e_pairs += p_
+            e_launch += nl
+        barrier()
+        e_wall = allmax(time.perf_counter() - t0)
+        e_pairs = allsum(float(e_pairs))
+        e2e = {"value": e_pairs / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 7 * 8 * n,
+               "ms_per_step": 1e3 * e_wall / args.steps,
+               "note": "set_mass (dirty -> full re-initialisation, as the reference's per-step mass channel forces) + evolve + get_state"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -121,8 +121,15 @@ int al26_grav_bench_force_n(al26_ctx *ctx, int64_t n_act, int reps, double *avg_
 /* tuning hook: pick one of the compiled force-kernel configurations (0 = default); applies at the
  * next al26_grav_commit */
 int al26_set_force_variant(al26_ctx *ctx, int variant);
+/* tuning hook: how block steps are driven on one GPU.  1 (default): one persistent cooperative kernel
+ * runs the whole predict -> force -> correct loop with grid barriers; 0: a CUDA graph of three kernels
+ * per block step (always used when world > 1, where NCCL calls sit between the kernels) */
+int al26_set_step_mode(al26_ctx *ctx, int mode);
 /* diagnostic: number of block steps by floor(log2(n_active)) since the last commit (32 bins) */
 int al26_grav_block_histogram(al26_ctx *ctx, int64_t *hist32);
+/* diagnostic: SM cycles CTA 0 of the persistent loop kernel spent in predict / barrier / force / barrier /
+ * correct / barrier since the last commit (6 values) */
+int al26_grav_loop_profile(al26_ctx *ctx, int64_t *cycles6);
 /* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
  * the roofline denominator of the force kernel */
 int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);

@@ -9,7 +9,7 @@ print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
 if os.environ.get("PROBE_VARIANTS"):
     n = 100000
     c = pkg.ic.cluster(n, seed=0)
-    for v in range(10):
+    for v in range(4):
         ctx.set_force_variant(v)
         g = pkg.GravityCore(ctx=ctx)
         g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
@@ -34,18 +34,28 @@ for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
     t, dt = g.get_timesteps()
     e, cnt = np.unique(np.log2(dt), return_counts=True)
     print("initial dt ladder:", dict(zip(e.astype(int).tolist(), cnt.tolist())))
-    k0, u0, s0 = g.energies()
-    tnow = 0.0
-    for lg in (-14, -12, -10, -8, -7):
-        span = 2.0 ** lg
-        tnow += span
-        t0 = time.perf_counter()
-        steps, pairs = g.evolve(tnow)
-        wall = time.perf_counter() - t0
-        ms, nl = g.last_device_ms()
-        print(f"  span 2^{lg}: {steps} block steps, {pairs:.3e} pairs, dev {ms:.2f} ms, wall {wall*1e3:.2f} ms, "
-              f"{pairs/ms*1e-6:.1f} Gpairs/s, {ms*1e3/max(steps,1):.1f} us/step, mean n_act {pairs/n/max(steps,1):.0f}, launches {nl}")
-        if wall > 60: break
-    print("  block-size histogram (log2 bins):", {b: h for b, h in enumerate(ctx.block_histogram()) if h})
-    k1, u1, _ = g.energies()
-    print("  dE/E", ((k0 + u0) - (k1 + u1)) / (k1 + u1), "t=", tnow)
+    for mode in (1, 0):
+        ctx.set_step_mode(mode)
+        g.set_time(0.0)
+        g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+        g.initialize()
+        k0, u0, s0 = g.energies()
+        tnow = 0.0
+        print(" step mode", "persistent loop" if mode else "graph")
+        for lg in (-14, -12, -10, -8, -7, -5):
+            span = 2.0 ** lg
+            tnow += span
+            t0 = time.perf_counter()
+            steps, pairs = g.evolve(tnow)
+            wall = time.perf_counter() - t0
+            ms, nl = g.last_device_ms()
+            print(f"  span 2^{lg}: {steps} block steps, {pairs:.3e} pairs, dev {ms:.2f} ms, wall {wall*1e3:.2f} ms, "
+                  f"{pairs/ms*1e-6:.1f} Gpairs/s, {ms*1e3/max(steps,1):.1f} us/step, mean n_act {pairs/n/max(steps,1):.0f}, launches {nl}")
+            if wall > 60: break
+        print("  block-size histogram (log2 bins):", {b: h for b, h in enumerate(ctx.block_histogram()) if h})
+        if mode:
+            pr = ctx.loop_profile(); nst = max(sum(ctx.block_histogram()), 1)
+            print("  loop kernel, CTA 0 cycles per block step:", {k: round(v / nst) for k, v in pr.items()})
+        k1, u1, _ = g.energies()
+        print("  dE/E", ((k0 + u0) - (k1 + u1)) / (k1 + u1), "t=", tnow)
+    ctx.set_step_mode(1)

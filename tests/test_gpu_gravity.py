@@ -22,11 +22,14 @@ def make(pkg, n, seed, model="plummer"):
     return [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
 
 
-@pytest.fixture()
-def grav(pkg, ctx):
+@pytest.fixture(params=[1, 0], ids=["loop", "graph"])
+def grav(pkg, ctx, request):
+    """Both ways of driving block steps: the persistent cooperative loop kernel and the CUDA graph."""
+    ctx.set_step_mode(request.param)
     g = pkg.GravityCore(ctx=ctx)  # the session shares one context: reset its clock and parameters
     g.set_time(0.0)
-    return g
+    yield g
+    ctx.set_step_mode(1)
 
 
 @pytest.mark.parametrize("n", [2, 3, 33, 257, 1000, 4096])
@@ -63,7 +66,7 @@ def test_force_subset_ragged_and_coincident(pkg, grav):
     assert vec_rel(out[:3], ref[:3]) < TOL and vec_rel(out[3:6], ref[3:6]) < TOL
 
 
-@pytest.mark.parametrize("variant", range(10))
+@pytest.mark.parametrize("variant", range(4))
 def test_force_variants_parity(pkg, ctx, variant):
     """every compiled force-kernel configuration, big blocks, ragged blocks and tiny (lane-split) blocks"""
     ctx.set_force_variant(variant)
