@@ -40,6 +40,9 @@ SIGNATURES = {
     "al26_device_info": (C.c_int, [_VP, _PINT, _PINT, _PI64, _PI64]),
     "al26_dist_unique_id": (C.c_int, [_VP]),
     "al26_dist_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "al26_dist_set_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_dist_p2p_export": (C.c_int, [_VP, _VP]),
+    "al26_dist_p2p_import": (C.c_int, [_VP, _VP, C.c_int]),
     "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
     "al26_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
     "al26_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
@@ -121,6 +124,7 @@ class Context:
         self.h = C.c_void_p(h)
         self.device = int(device)
         self.rank, self.world = 0, 1
+        self.dist_mode, self.exchange = None, None
 
     def close(self):
         if getattr(self, "h", None):
@@ -141,10 +145,28 @@ class Context:
         self.chk(self.L.al26_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(fr), C.byref(tot)))
         return {"sm_count": sm.value, "clock_khz": khz.value, "free_bytes": fr.value, "total_bytes": tot.value}
 
-    def dist_init(self, rank, world, unique_id_bytes):
+    def dist_init(self, rank, world, unique_id_bytes, mode="p2p", exchange=None):
+        """mode "p2p": peer-memory exchange (default), "nccl": all-gather path.  `exchange(bytes) -> list of
+        bytes` all-gathers a 64-byte blob across ranks (dist.py provides one over torch.distributed); it is
+        called after every gravity commit in p2p mode."""
+        self.chk(self.L.al26_dist_set_mode(self.h, 1 if mode == "p2p" else 0))
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
         self.chk(self.L.al26_dist_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p) if buf else None))
         self.rank, self.world = int(rank), int(world)
+        self.dist_mode = mode if world > 1 else None
+        self.exchange = exchange
+
+    def p2p_connect(self):
+        """after a gravity commit in p2p mode: swap CUDA IPC handles of the staging slabs"""
+        if self.world == 1 or self.dist_mode != "p2p":
+            return
+        if self.exchange is None:
+            raise Al26Error(-2, "peer-memory mode needs an exchange function (see dist.init_context)")
+        mine = C.create_string_buffer(64)
+        self.chk(self.L.al26_dist_p2p_export(self.h, C.cast(mine, C.c_void_p)))
+        blobs = self.exchange(mine.raw)
+        allh = C.create_string_buffer(b"".join(blobs), 64 * self.world)
+        self.chk(self.L.al26_dist_p2p_import(self.h, C.cast(allh, C.c_void_p), self.world))
 
     def set_force_variant(self, v):
         self.chk(self.L.al26_set_force_variant(self.h, int(v)))

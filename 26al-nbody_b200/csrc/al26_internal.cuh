@@ -35,10 +35,47 @@ struct GravHeader {
   int loop_error;            // raised when a barrier spin limit is hit
   int phase;                 // StepCtrl phase after the last loop-kernel launch
   int pad2;
+  unsigned long long dist_step;  // id of the last block step completed in peer-memory mode
+  unsigned long long dist_tnext_bits;  // the global next block time after it
   long long loop_cycles[6];  // diagnostic: CTA 0's SM cycles in predict / barrier / force / barrier / correct / barrier
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
+
+// ---- peer-memory multi-GPU mode: every rank holds the full state; a rank corrects the
+// active particles it owns (i % world == rank) and stores their new state straight into EVERY rank's staging
+// slab over NVLink; staged records are pulled into the local state by the next predictor pass.  One slab per
+// rank (one cudaMalloc, exported with CUDA IPC): two parities of {pos, vel, acc, jrk, t, dt, tag} for all N
+// particles, then the mailbox used by the cross-GPU barrier.
+constexpr int MAX_PEERS = 8;
+struct StagingView {
+  double4 *pos, *vel, *acc, *jrk;
+  double *t, *dt;
+  unsigned int *tag;  // id of the block step that wrote the record
+};
+struct MboxEntry {
+  unsigned long long tmin_bits;  // sender's min(t+dt) candidate for the next block time
+  unsigned long long tag;        // id of the block step the sender has completed
+};
+__host__ __device__ inline size_t staging_parity_bytes(int n) {
+  return ((size_t)n * (4 * 32 + 2 * 8 + 4) + 255) & ~(size_t)255;
+}
+__host__ __device__ inline StagingView staging_view(void *slab, int n, int parity) {
+  char *b = (char *)slab + (size_t)parity * staging_parity_bytes(n);
+  StagingView v;
+  v.pos = (double4 *)b;
+  v.vel = v.pos + n;
+  v.acc = v.vel + n;
+  v.jrk = v.acc + n;
+  v.t = (double *)(v.jrk + n);
+  v.dt = v.t + n;
+  v.tag = (unsigned int *)(v.dt + n);
+  return v;
+}
+__host__ __device__ inline MboxEntry *mbox_of(void *slab, int n) {
+  return (MboxEntry *)((char *)slab + 2 * staging_parity_bytes(n));
+}
+inline size_t slab_bytes(int n) { return 2 * staging_parity_bytes(n) + 2 * MAX_PEERS * sizeof(MboxEntry) + 256; }
 
 struct GravDev {
   int n_loc;  // particles owned by this rank
@@ -59,6 +96,9 @@ struct GravDev {
   GravHeader *hdr;
   // MODE_RAW outputs (parity hook al26_grav_force)
   double4 *raw_a, *raw_j;
+  // peer-memory mode
+  int rank, world, p2p;
+  void *slab[MAX_PEERS];  // slab[q]: rank q's staging slab as mapped in this process (slab[rank] = own)
 };
 
 // ---- work decomposition of one force evaluation, a pure function of (n_act, n_tot, grid) so
@@ -156,6 +196,9 @@ int force_variant_info(int v, int *ctas_per_sm, int *ipt);
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
 cudaError_t force_kernel_setup();
 int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cudaError_t *err);
+int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsigned long long step_id0,
+                     cudaStream_t s, cudaError_t *err);
+int launch_pull(const GravDev &g, unsigned long long step_id, cudaStream_t s);
 cudaError_t loop_kernel_setup();
 int loop_max_ctas_per_sm(int variant);
 

@@ -78,6 +78,10 @@ struct al26_ctx {
   // dist
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  int dist_mode = 1;             // world > 1: 1 = peer-memory (NVLink) exchange inside the loop kernel, 0 = NCCL graph path
+  void *slab = nullptr;          // own staging slab (peer-memory mode)
+  bool p2p_ready = false;        // peers' slabs imported
+  unsigned long long dist_step = 0;
 
   // gravity
   GravDev g{};
@@ -114,6 +118,8 @@ struct al26_ctx {
 };
 
 namespace {
+
+inline bool is_p2p(const al26_ctx *c) { return c->world > 1 && c->dist_mode == 1; }
 
 int fail(al26_ctx *c, int code, const char *fmt, ...) {
   char buf[512];
@@ -237,6 +243,11 @@ void free_gravity(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   c->graph = nullptr;
   GravDev &g = c->g;
+  for (int q = 0; q < MAX_PEERS; q++)
+    if (g.slab[q] && q != c->rank && c->p2p_ready) cudaIpcCloseMemHandle(g.slab[q]);
+  if (c->slab) cudaFree(c->slab);
+  c->slab = nullptr;
+  c->p2p_ready = false;
   void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr,
                   (void *)g.decomp_tab};
   for (void *p : ptrs)
@@ -268,7 +279,7 @@ void slice_of(int64_t n, int rank, int world, int64_t &i0, int64_t &nloc) {
 // slice into a padded layout would waste bandwidth; instead require equal slices (n % world == 0
 // is enforced at commit) and use one in-place ncclAllGather per array.
 int gather_j(al26_ctx *c) {
-  if (c->world == 1) return 0;
+  if (c->world == 1 || is_p2p(c)) return 0;  // peer-memory mode: the state is replicated, nothing to gather
   const GravDev &g = c->g;
   const size_t cnt = (size_t)g.n_loc * 4;  // doubles per rank
   NC(g_nccl.GroupStart());
@@ -279,7 +290,7 @@ int gather_j(al26_ctx *c) {
 }
 // global minimum of the next block time (one 8-byte all-reduce); no-op on one GPU
 int reduce_tnext(al26_ctx *c, int phase) {
-  if (c->world == 1) return 0;
+  if (c->world == 1 || is_p2p(c)) return 0;
   unsigned long long *p = &c->g.ctrl[phase].t_next_bits;
   NC(g_nccl.AllReduce(p, p, 1, ncclUint64, ncclMin, c->comm, c->stream));
   return 0;
@@ -304,6 +315,7 @@ constexpr int GRAPH_ROUNDS = 8;  // 3 phases x 8 = 24 block steps per graph laun
 int build_graph(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   c->graph = nullptr;
+  if (is_p2p(c)) return 0;  // the peer-memory path runs entirely inside the loop kernel
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   const int64_t l0 = c->launches;
@@ -331,9 +343,15 @@ int reset_ctrl(al26_ctx *c, int zero_counters) {
 }
 
 // forces + initial timesteps on every local particle (the "dirty" path)
+int dist_single(al26_ctx *c, int mode);
 int initialise_forces(al26_ctx *c) {
-  reset_ctrl(c, 0);
-  int rc = enqueue_step(c, MODE_INIT, 0);
+  int rc;
+  if (is_p2p(c)) {
+    rc = dist_single(c, MODE_INIT);
+  } else {
+    reset_ctrl(c, 0);
+    rc = enqueue_step(c, MODE_INIT, 0);
+  }
   if (rc) return rc;
   c->dirty = false;
   return 0;
@@ -365,6 +383,30 @@ int run_loop(al26_ctx *c, int max_steps) {
   return 0;
 }
 
+// peer-memory mode: up to max_steps block steps (or the single init / sync step) in one cooperative launch
+int run_dist(al26_ctx *c, int mode, int max_steps) {
+  if (!c->p2p_ready) return fail(c, AL26_ESTATE, "peer-memory mode: peers' slabs not imported (al26_dist_p2p_import)");
+  k_loop_prepare<<<1, 1, 0, c->stream>>>(c->g.hdr);
+  cudaError_t e = cudaSuccess;
+  c->launches += 1 + launch_loop_dist(c->g, mode, c->dbg_phase, max_steps, c->dist_step, c->stream, &e);
+  if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the peer-memory loop kernel failed: %s", cudaGetErrorString(e));
+  int rc = read_header(c);
+  if (rc) return rc;
+  if (c->h_hdr->loop_error) return fail(c, AL26_ECUDA, "peer-memory loop kernel: barrier spin limit hit (code %d)", c->h_hdr->loop_error);
+  c->dbg_phase = c->h_hdr->phase;
+  c->dist_step = c->h_hdr->dist_step;
+  return 0;
+}
+// one init or sync step in peer-memory mode, then pull what was staged into the local state
+int dist_single(al26_ctx *c, int mode) {
+  reset_ctrl(c, 0);
+  c->dbg_phase = 0;
+  int rc = run_dist(c, mode, 1);
+  if (rc) return rc;
+  c->launches += launch_pull(c->g, c->dist_step, c->stream);
+  return 0;
+}
+
 int begin_evolve(al26_ctx *c, double t_end) {
   if (!c->committed) return fail(c, AL26_ESTATE, "evolve before commit");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "evolve already in progress");
@@ -390,8 +432,13 @@ int begin_evolve(al26_ctx *c, double t_end) {
 }
 
 int finish_evolve(al26_ctx *c) {
-  reset_ctrl(c, 0);
-  int rc = enqueue_step(c, MODE_SYNC, 0);
+  int rc;
+  if (is_p2p(c)) {
+    rc = dist_single(c, MODE_SYNC);
+  } else {
+    reset_ctrl(c, 0);
+    rc = enqueue_step(c, MODE_SYNC, 0);
+  }
   if (rc) return rc;
   // times are relative to the start of an evolve call: everybody is synchronised, so tau = 0
   CU(cudaMemsetAsync(c->g.t, 0, (size_t)c->g.n_loc * sizeof(double), c->stream));
@@ -511,6 +558,7 @@ int al26_dist_init(al26_ctx *c, int rank, int world, const void *uid) {
     c->world = 1;
     return 0;
   }
+  if (world > MAX_PEERS && c->dist_mode == 1) return fail(c, AL26_EINVAL, "peer-memory mode supports at most %d ranks", MAX_PEERS);
   if (!uid) return fail(c, AL26_EINVAL, "null nccl unique id");
   std::string why;
   if (!load_nccl(why)) return fail(c, AL26_ENCCL, "%s", why.c_str());
@@ -520,6 +568,42 @@ int al26_dist_init(al26_ctx *c, int rank, int world, const void *uid) {
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
+  return 0;
+}
+
+int al26_dist_set_mode(al26_ctx *c, int mode) {
+  if (!c) return AL26_EINVAL;
+  if (mode != 0 && mode != 1) return fail(c, AL26_EINVAL, "dist mode must be 0 (NCCL) or 1 (peer memory)");
+  if (c->committed || c->e_committed) return fail(c, AL26_ESTATE, "al26_dist_set_mode must precede commit");
+  c->dist_mode = mode;
+  return 0;
+}
+
+int al26_dist_p2p_export(al26_ctx *c, void *out64) {
+  if (!c || !out64) return AL26_EINVAL;
+  if (!is_p2p(c) || !c->committed || !c->slab) return fail(c, AL26_ESTATE, "p2p_export needs a committed peer-memory context");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->slab));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &h, 64);
+  return 0;
+}
+
+int al26_dist_p2p_import(al26_ctx *c, const void *handles, int world) {
+  if (!c || !handles) return AL26_EINVAL;
+  if (!is_p2p(c) || !c->committed) return fail(c, AL26_ESTATE, "p2p_import needs a committed peer-memory context");
+  if (world != c->world || world > MAX_PEERS) return fail(c, AL26_EINVAL, "p2p_import: world %d (context %d, max %d)", world, c->world, MAX_PEERS);
+  CU(cudaSetDevice(c->device));
+  for (int q = 0; q < world; q++) {
+    if (q == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + 64 * q, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->g.slab[q] = p;
+  }
+  c->p2p_ready = true;
   return 0;
 }
 
@@ -549,8 +633,19 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   free_gravity(c);
   int64_t i0, nloc;
   slice_of(n, c->rank, c->world, i0, nloc);
+  if (is_p2p(c)) {  // replicated state: every rank holds all n particles, owns i % world == rank
+    i0 = 0;
+    nloc = n;
+  }
   GravDev &g = c->g;
   g.n_tot = (int)n; g.n_loc = (int)nloc; g.i0 = (int)i0;
+  g.rank = c->rank; g.world = c->world; g.p2p = is_p2p(c) ? 1 : 0;
+  if (is_p2p(c)) {
+    CU(cudaMalloc(&c->slab, slab_bytes((int)n)));
+    CU(cudaMemset(c->slab, 0, slab_bytes((int)n)));
+    g.slab[c->rank] = c->slab;
+    c->dist_step = 0;
+  }
   {
     int minb = 2, ipt = 2;
     force_variant_info(c->force_variant, &minb, &ipt);
@@ -660,7 +755,12 @@ int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t 
   CU(cudaEventRecord(c->ev0, c->stream));
   int rc = begin_evolve(c, t_end);
   if (rc) return rc;
-  if (use_loop(c)) {
+  if (is_p2p(c)) {
+    while (true) {
+      if ((rc = run_dist(c, MODE_STEP, 1 << 30))) { c->in_evolve = false; return rc; }
+      if (c->h_hdr->done) break;
+    }
+  } else if (use_loop(c)) {
     while (true) {
       if ((rc = run_loop(c, 1 << 30))) { c->in_evolve = false; return rc; }
       if (c->h_hdr->done) break;
@@ -712,8 +812,8 @@ int al26_grav_dbg_advance(al26_ctx *c, int64_t max_steps, int64_t *n_done, int *
     int rc = read_header(c);
     if (rc) return rc;
     const long long before = c->h_hdr->n_steps;
-    if (use_loop(c)) {
-      if ((rc = run_loop(c, 1))) return rc;
+    if (is_p2p(c) || use_loop(c)) {
+      if ((rc = (is_p2p(c) ? run_dist(c, MODE_STEP, 1) : run_loop(c, 1)))) return rc;
       if (c->h_hdr->done) {
         fin = 1;
         break;
@@ -865,7 +965,7 @@ int al26_grav_energies(al26_ctx *c, double *kinetic, double *potential, double *
   c->launches += launch_snapshot_j(g, c->stream);
   int rc = gather_j(c);
   if (rc) return rc;
-  const size_t need = (size_t)energy_grid(g.n_loc) * 3 + 2 * ((size_t)1184 * 256 + (size_t)g.n_loc + 512) + 64;
+  const size_t need = (size_t)energy_grid(g.n_loc) * 3 + 2 * ((size_t)1184 * 256 + (size_t)g.n_loc + 512) + 64;  // sized for n_loc >= the slice
   if (c->en_scratch_doubles < need) {
     if (c->en_scratch) cudaFree(c->en_scratch);
     c->en_scratch = nullptr;
@@ -876,6 +976,11 @@ int al26_grav_energies(al26_ctx *c, double *kinetic, double *potential, double *
   EnergyDev e;
   e.n_loc = g.n_loc; e.n_tot = g.n_tot; e.i0 = g.i0; e.eps2 = c->eps2;
   e.pos = g.pos; e.vel = g.vel; e.jpos = g.jpos;
+  if (is_p2p(c)) {  // replicated state: each rank sums its contiguous share of the i-particles
+    int64_t s0, sl;
+    slice_of(g.n_tot, c->rank, c->world, s0, sl);
+    e.n_loc = (int)sl; e.i0 = (int)s0; e.pos = g.pos + s0; e.vel = g.vel + s0;
+  }
   e.block_part = c->en_scratch; e.out = c->en_out;
   c->launches += launch_energies(e, c->stream);
   if (c->world > 1) NC(g_nccl.AllReduce(c->en_out, c->en_out, 3, ncclDouble, ncclSum, c->comm, c->stream));

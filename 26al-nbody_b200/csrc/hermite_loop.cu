@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, c
       if (first) g.hdr->done = 1;
       break;
     }
-    phase_predict_list<MODE_STEP>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh);
+    phase_predict_list<MODE_STEP, false>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh);
     if (first) {
       old->t_next_bits = INF_BITS;
       old->n_act = 0;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, c
     if (!grid_barrier(g.hdr, target, n_ctas)) break;
     PROF(3)
     // ---- phase C: reduce partials, corrector, ladder, next block time -------------------------
-    if (n_act > 0) phase_correct<MODE_STEP>(g, cur, nxt, n_act, blockIdx.x, n_ctas, sh, shr);
+    if (n_act > 0) phase_correct<MODE_STEP, false>(g, nxt, n_act, tn, blockIdx.x, n_ctas, sh, shr);
     PROF(4)
     if (!grid_barrier(g.hdr, target, n_ctas)) break;
     PROF(5)
@@ -108,6 +108,168 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, c
     g.hdr->phase = ph;
     for (int k = 0; k < 6; k++) g.hdr->loop_cycles[k] += prof[k];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory multi-GPU loop.  Every rank runs this kernel on its own GPU at the same
+// time.  Per block step: predict ALL particles locally (pulling the records peers staged in the previous
+// step), force on the active particles this rank owns, corrector, and the corrected particles are stored
+// straight into every rank's staging slab over NVLink.  The third barrier of the step is a cross-GPU one:
+// the last CTA of a rank to arrive (so everything the rank wrote is fenced at system scope) posts the rank's
+// candidate for the next block time plus the step id into every rank's mailbox; every CTA then waits until
+// all `world` mailbox entries carry this step id.  No NCCL, no host, one NVLink round per block step.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// returns false on error; tmin_out = global minimum of the ranks' candidates (the next block time)
+__device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target, const unsigned n_ctas,
+                                             const unsigned long long step_id, const StepCtrl *nxt,
+                                             unsigned long long *sh_tmin, unsigned long long &tmin_out) {
+  GravHeader *hdr = g.hdr;
+  const int par = (int)(step_id & 1ull);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    target += n_ctas;
+    const unsigned old = atomicAdd(&hdr->bar_counter, 1u);
+    if (old == target - 1u) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
+      __threadfence_system();
+      const unsigned long long lm = ld_volatile_u64(&nxt->t_next_bits);
+      for (int q = 0; q < g.world; q++) st_volatile_u64(&(mbox_of(g.slab[q], g.n_tot) + par * MAX_PEERS + g.rank)->tmin_bits, lm);
+      __threadfence_system();
+      for (int q = 0; q < g.world; q++) st_volatile_u64(&(mbox_of(g.slab[q], g.n_tot) + par * MAX_PEERS + g.rank)->tag, step_id);
+    }
+    const MboxEntry *mine = mbox_of(g.slab[g.rank], g.n_tot) + par * MAX_PEERS;
+    unsigned spins = 0;
+    bool ok = true;
+    for (int q = 0; q < g.world && ok; q++) {
+      while (ld_volatile_u64(&mine[q].tag) != step_id) {
+        if (++spins > LOOP_SPIN_LIMIT) {
+          atomicExch(&hdr->loop_error, 2);
+          ok = false;
+          break;
+        }
+        if ((spins & 0xfff) == 0 && ld_volatile_u32((const unsigned *)&hdr->loop_error)) {
+          ok = false;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    unsigned long long tm = INF_BITS;
+    for (int q = 0; q < g.world; q++) {
+      const unsigned long long v = ld_volatile_u64(&mine[q].tmin_bits);
+      tm = v < tm ? v : tm;
+    }
+    *sh_tmin = tm;
+  }
+  __syncthreads();
+  tmin_out = *sh_tmin;
+  return ld_volatile_u32((const unsigned *)&hdr->loop_error) == 0;
+}
+
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    k_loop_dist(const GravDev g, const int phase0, const int max_steps, const unsigned long long step_id0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
+  __shared__ unsigned long long sh[C::THREADS / 32];
+  __shared__ double shr[C::THREADS / 32][7];
+  __shared__ unsigned long long sh_tmin;
+  const unsigned n_ctas = gridDim.x;
+  const bool first = (blockIdx.x == 0 && threadIdx.x == 0);
+  force_smem_init<C>(sm);
+  uint32_t it = 0;
+  unsigned target = 0;
+  int ph = phase0;
+  const double span = g.hdr->span;
+  unsigned long long step_id = step_id0;   // id of the last completed step; this launch starts with step_id0 + 1
+  // the next block time: written by k_begin (identical on every rank: the state is replicated) or by the
+  // previous launch
+  unsigned long long tnext_bits = __ldcg(&g.ctrl[phase0].t_next_bits);
+  for (int step = 0; step < max_steps; step++) {
+    StepCtrl *cur = &g.ctrl[ph];
+    StepCtrl *nxt = &g.ctrl[(ph + 1) % 3];
+    StepCtrl *old = &g.ctrl[(ph + 2) % 3];
+    double tn;
+    if (MODE == MODE_STEP) {
+      tn = bitsd(tnext_bits);
+      if (tn > span) {
+        if (first) g.hdr->done = 1;
+        break;
+      }
+    } else if (MODE == MODE_INIT) {
+      tn = 0.0;
+    } else {
+      tn = span;
+    }
+    const unsigned long long this_id = step_id + 1;
+    phase_predict_list<MODE, true>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh, step_id);
+    if (first) {
+      old->t_next_bits = INF_BITS;
+      old->n_act = 0;
+      old->work_counter = 0;
+    }
+    if (!grid_barrier(g.hdr, target, n_ctas)) break;
+    const int n_act = __ldcg(&cur->n_act);
+    if (n_act > 0) force_items<C>(g, sm, cur, n_act, n_ctas, it);
+    if (!grid_barrier(g.hdr, target, n_ctas)) break;
+    if (n_act > 0) phase_correct<MODE, true>(g, nxt, n_act, tn, blockIdx.x, n_ctas, sh, shr, this_id);
+    if (!dist_barrier(g, target, n_ctas, this_id, nxt, &sh_tmin, tnext_bits)) break;
+    step_id = this_id;
+    ph = (ph + 1) % 3;
+    if (first) g.ctrl[ph].t_next_bits = tnext_bits;  // the global next block time, for the host / the next launch
+  }
+  if (first) {
+    g.hdr->phase = ph;
+    g.hdr->dist_step = step_id;
+    g.hdr->dist_tnext_bits = tnext_bits;
+  }
+}
+
+// pull the records staged during block step `step_id` into the local state (after an init / sync step)
+__global__ void __launch_bounds__(256) k_pull(const GravDev g, const unsigned long long step_id) {
+  const StagingView sv = staging_view(g.slab[g.rank], g.n_tot, (int)(step_id & 1ull));
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_loc && sv.tag[i] == (unsigned int)step_id) {
+    g.pos[i] = sv.pos[i]; g.vel[i] = sv.vel[i]; g.acc[i] = sv.acc[i]; g.jrk[i] = sv.jrk[i];
+    g.t[i] = sv.t[i]; g.dt[i] = sv.dt[i];
+    sv.tag[i] = 0u;  // consumed: the next predictor pass must not pull it again (k_begin edits t / dt in between)
+  }
+}
+
+int launch_pull(const GravDev &g, unsigned long long step_id, cudaStream_t s) {
+  k_pull<<<(g.n_loc + 255) / 256, 256, 0, s>>>(g, step_id);
+  return 1;
+}
+
+template <class C>
+static cudaError_t launch_loop_dist_t(const GravDev &g, int mode, void **args, cudaStream_t s) {
+  const void *fn = mode == MODE_STEP ? (const void *)k_loop_dist<C, MODE_STEP>
+                   : mode == MODE_INIT ? (const void *)k_loop_dist<C, MODE_INIT> : (const void *)k_loop_dist<C, MODE_SYNC>;
+  return cudaLaunchCooperativeKernel(fn, dim3(g.grid_force), dim3(C::THREADS), args, sizeof(ForceSmemT<C>), s);
+}
+
+int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsigned long long step_id0,
+                     cudaStream_t s, cudaError_t *err) {
+  GravDev gg = g;
+  void *args[] = {(void *)&gg, (void *)&phase, (void *)&max_steps, (void *)&step_id0};
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (g.variant) {
+#define X(id, cfg) case id: e = launch_loop_dist_t<cfg>(g, mode, args, s); break;
+    FOR_EACH_FORCE_VARIANT(X)
+#undef X
+  }
+  if (err) *err = e;
+  return 1;
 }
 
 int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cudaError_t *err) {
@@ -129,7 +291,11 @@ int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cuda
 
 cudaError_t loop_kernel_setup() {
   cudaError_t e = cudaSuccess;
-#define X(id, cfg) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loop<cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>));
+#define X(id, cfg)                                                                                                  \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loop<cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>)); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loop_dist<cfg, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>)); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loop_dist<cfg, MODE_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>)); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loop_dist<cfg, MODE_SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ForceSmemT<cfg>));
   FOR_EACH_FORCE_VARIANT(X)
 #undef X
   return e;

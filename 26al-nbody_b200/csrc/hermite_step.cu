@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_predict_list(const GravDev g, co
   } else {
     tn = g.hdr->span;
   }
-  phase_predict_list<MODE>(g, cur, nxt, tn, blockIdx.x, gridDim.x, sh);
+  phase_predict_list<MODE, false>(g, cur, nxt, tn, blockIdx.x, gridDim.x, sh);
   if (first) {
     old->t_next_bits = INF_BITS;
     old->n_act = 0;
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_correct(const GravDev g, const i
   StepCtrl *nxt = &g.ctrl[(phase + 1) % 3];
   const int n_act = cur->n_act;
   if (n_act <= 0) return;
-  phase_correct<MODE>(g, cur, nxt, n_act, blockIdx.x, gridDim.x, sh, shr);
+  const double tn = (MODE == MODE_STEP) ? bitsd(cur->t_next_bits) : g.hdr->span;
+  phase_correct<MODE, false>(g, nxt, n_act, tn, blockIdx.x, gridDim.x, sh, shr);
 }
 
 static inline int blocks_for(int n) { return (n + ST_THREADS - 1) / ST_THREADS; }

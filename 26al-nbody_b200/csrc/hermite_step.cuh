@@ -57,17 +57,31 @@ __device__ __forceinline__ void block_min_to(unsigned long long v, unsigned long
 // Predict every local particle to `tn` into the global j-set, build the active list of this step in
 // cur->n_act / g.list, and fold min(t+dt) of the non-active particles into nxt->t_next_bits.
 // (block_id, n_blocks) describe the caller's grid; every block runs the same number of iterations.
-template <int MODE>
+// DIST (peer-memory mode): the state is replicated; first pull the records peers staged during block step
+// `pull_tag` (parity pull_tag & 1) into the local state, and list only the active particles this rank owns.
+template <int MODE, bool DIST>
 __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
-                                                   const int block_id, const int n_blocks, unsigned long long *sh) {
+                                                   const int block_id, const int n_blocks, unsigned long long *sh,
+                                                   const unsigned long long pull_tag = 0) {
   const int nthr = blockDim.x;
   unsigned long long c_min = INF_BITS;
+  StagingView sv;
+  if (DIST) sv = staging_view(g.slab[g.rank], g.n_tot, (int)(pull_tag & 1ull));
   for (int base = block_id * nthr; base < g.n_loc; base += n_blocks * nthr) {
     const int i = base + threadIdx.x;
     bool active = false;
     if (i < g.n_loc) {
-      const double4 p = g.pos[i], v = g.vel[i], a = g.acc[i], j = g.jrk[i];
-      const double ti = g.t[i], dti = g.dt[i];
+      double4 p, v, a, j;
+      double ti, dti;
+      if (DIST && pull_tag != 0ull && sv.tag[i] == (unsigned int)pull_tag) {  // staged by its owner in the previous block step
+        p = sv.pos[i]; v = sv.vel[i]; a = sv.acc[i]; j = sv.jrk[i];
+        ti = sv.t[i]; dti = sv.dt[i];
+        g.pos[i] = p; g.vel[i] = v; g.acc[i] = a; g.jrk[i] = j;
+        g.t[i] = ti; g.dt[i] = dti;
+      } else {
+        p = g.pos[i]; v = g.vel[i]; a = g.acc[i]; j = g.jrk[i];
+        ti = g.t[i]; dti = g.dt[i];
+      }
       const double s = (MODE == MODE_INIT) ? 0.0 : (tn - ti);  // init: predicted == current, whatever t holds
       const double s2 = s * s * 0.5, s3 = s * s * s * (1.0 / 6.0);
       double4 pp, pv;
@@ -89,6 +103,7 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
         const unsigned long long cb = dbits(c);
         c_min = cb < c_min ? cb : c_min;
       }
+      if (DIST && (i % g.world) != g.rank) active = false;  // somebody else's particle
     }
     // ballot compaction (order within the list is irrelevant to the results: every slot's force sum
     // runs over j in a fixed order)
@@ -117,10 +132,32 @@ __device__ __forceinline__ double aarseth(const double eta, const double a1[3], 
   return eta * sqrt(num / den);
 }
 
-// corrector + ladder for one active slot, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}
-template <int MODE>
-__device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur, const int slot, const double r[7],
-                                           unsigned long long &c_bits) {
+struct NewState {
+  double4 pos, vel, acc, jrk;
+  double t, dt;
+};
+
+// where a corrected particle goes: the local state, or (peer-memory mode) every rank's staging slab
+template <bool DIST>
+__device__ __forceinline__ void store_state(const GravDev &g, const int i, const NewState &n, const unsigned long long step_id) {
+  if (!DIST) {
+    g.pos[i] = n.pos; g.vel[i] = n.vel; g.acc[i] = n.acc; g.jrk[i] = n.jrk;
+    g.t[i] = n.t; g.dt[i] = n.dt;
+  } else {
+    for (int q = 0; q < g.world; q++) {  // NVLink peer stores (q == rank: local)
+      const StagingView v = staging_view(g.slab[q], g.n_tot, (int)(step_id & 1ull));
+      v.pos[i] = n.pos; v.vel[i] = n.vel; v.acc[i] = n.acc; v.jrk[i] = n.jrk;
+      v.t[i] = n.t; v.dt[i] = n.dt;
+      v.tag[i] = (unsigned int)step_id;
+    }
+  }
+}
+
+// corrector + ladder for one active slot, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}; tn = the
+// block time (MODE_STEP) or the span (MODE_SYNC)
+template <int MODE, bool DIST>
+__device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, const int slot, const double r[7],
+                                           unsigned long long &c_bits, const unsigned long long step_id) {
   if (MODE == MODE_RAW) {
     g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
     g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
@@ -129,9 +166,10 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur
   const int i = g.list[slot];
   const double a1[3] = {r[0], r[1], r[2]};
   const double j1[3] = {r[3], r[4], r[5]};
+  NewState n;
+  n.acc = make_double4(a1[0], a1[1], a1[2], r[6]);
+  n.jrk = make_double4(j1[0], j1[1], j1[2], 0.0);
   if (MODE == MODE_INIT) {
-    g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
-    g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
     const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
     const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
     double dt0 = g.dt_max;
@@ -140,14 +178,20 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur
     if (dt0 > g.dt_max) dt0 = g.dt_max;
     double dd = pow2floor(dt0);
     if (dd < g.dt_min) dd = g.dt_min;
-    g.dt[i] = dd;
-    g.t[i] = 0.0;
+    n.dt = dd;
+    n.t = 0.0;
+    if (!DIST) {  // positions and velocities are untouched
+      g.acc[i] = n.acc; g.jrk[i] = n.jrk; g.dt[i] = n.dt; g.t[i] = n.t;
+    } else {
+      n.pos = g.pos[i];
+      n.vel = g.vel[i];
+      store_state<true>(g, i, n, step_id);
+    }
     return;
   }
   const double4 a0v = g.acc[i], j0v = g.jrk[i];
   const double4 xpv = g.jpos[g.i0 + i], vpv = g.jvel[g.i0 + i];
   const double ti = g.t[i], dti = g.dt[i];
-  const double tn = (MODE == MODE_STEP) ? bitsd(cur->t_next_bits) : g.hdr->span;
   const double s = (MODE == MODE_STEP) ? dti : (tn - ti);
   const double a0[3] = {a0v.x, a0v.y, a0v.z}, j0[3] = {j0v.x, j0v.y, j0v.z};
   const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
@@ -164,11 +208,8 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur
     a2[c] = (2.0 * alpha + 6.0 * beta) * is2;
     a3[c] = (6.0 * beta) * is3;
   }
-  const double m = g.pos[i].w;
-  g.pos[i] = make_double4(x1[0], x1[1], x1[2], m);
-  g.vel[i] = make_double4(v1[0], v1[1], v1[2], 0.0);
-  g.acc[i] = make_double4(a1[0], a1[1], a1[2], r[6]);
-  g.jrk[i] = make_double4(j1[0], j1[1], j1[2], 0.0);
+  n.pos = make_double4(x1[0], x1[1], x1[2], xpv.w);  // jpos.w carries the mass
+  n.vel = make_double4(v1[0], v1[1], v1[2], 0.0);
   double dtA = aarseth(g.eta, a1, j1, a2, a3);
   double nd;
   if (MODE == MODE_STEP) {
@@ -179,17 +220,16 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur
       const double q = tn / (2.0 * dti);
       if (q == floor(q)) nd = 2.0 * dti;
     }
-    g.t[i] = tn;
-    g.dt[i] = nd;
     const unsigned long long cb = dbits(tn + nd);
     c_bits = cb < c_bits ? cb : c_bits;
   } else {  // MODE_SYNC
     if (dtA > g.dt_max) dtA = g.dt_max;
     nd = pow2floor(dtA);
     if (nd < g.dt_min) nd = g.dt_min;
-    g.t[i] = tn;
-    g.dt[i] = nd;
   }
+  n.t = tn;
+  n.dt = nd;
+  store_state<DIST>(g, i, n, step_id);
 }
 
 // Reduction of the j-chunk partials in a FIXED order, then the corrector.
@@ -197,10 +237,10 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const StepCtrl *cur
 //   many chunks (tiny blocks cut into up to `grid` chunks): one CTA per slot, all threads load in
 //   parallel (one round trip instead of n_jsplit/32 dependent ones), butterfly + ordered warp sum.
 // sh: blockDim/32 u64, shr: blockDim/32 x 7 doubles of shared memory.
-template <int MODE>
-__device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const int n_act,
+template <int MODE, bool DIST>
+__device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, const int n_act, const double tn,
                                               const int block_id, const int n_blocks, unsigned long long *sh,
-                                              double (*shr)[7]) {
+                                              double (*shr)[7], const unsigned long long step_id = 0) {
   const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -232,7 +272,7 @@ __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *cur, S
           for (int w = 1; w < wpb; w++) a += shr[w][c];
           r[c] = a;
         }
-        apply_slot<MODE>(g, cur, slot, r, c_bits);
+        apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id);
       }
     }
   } else {
@@ -249,7 +289,7 @@ __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *cur, S
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
       }
-      if (lane == 0) apply_slot<MODE>(g, cur, slot, r, c_bits);
+      if (lane == 0) apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id);
     }
   }
   if (MODE == MODE_STEP) block_min_to(c_bits, &nxt->t_next_bits, sh);

@@ -35,10 +35,23 @@ def broadcast_unique_id(make_uid, rank, device="cpu", group=None):
     return buf.cpu().numpy().tobytes()
 
 
-def init_context(ctx, rank, world, device="cuda", group=None):
-    """Join `ctx` (an al26 Context on this rank's GPU) to the job's NCCL communicator."""
+def allgather_bytes(blob, world, device="cpu", group=None):
+    """All-gather one fixed-size byte string per rank (the CUDA IPC handles of the staging slabs)."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return [p.cpu().numpy().tobytes() for p in parts]
+
+
+def init_context(ctx, rank, world, device="cuda", group=None, mode="p2p"):
+    """Join `ctx` (an al26 Context on this rank's GPU) to the job: NCCL communicator (energies, and the
+    all-gather path when mode == "nccl") plus, in the default peer-memory mode, the hook that swaps the
+    staging slabs' IPC handles after every commit."""
     if world == 1:
         return ctx
     uid = broadcast_unique_id(_lib.dist_unique_id, rank, device=device, group=group)
-    ctx.dist_init(rank, world, uid)
+    ctx.dist_init(rank, world, uid, mode=mode,
+                  exchange=lambda blob: allgather_bytes(blob, world, device=device, group=group))
     return ctx

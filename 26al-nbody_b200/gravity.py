@@ -44,6 +44,7 @@ class GravityCore:
             raise ValueError("commit: arrays differ in length")
         self.ctx.chk(self.L.al26_grav_commit(self.h, n, *arrs))
         self.n = n
+        self.ctx.p2p_connect()  # multi-GPU peer-memory mode: swap the staging slabs' IPC handles
 
     def set_mass(self, m):
         self.ctx.chk(self.L.al26_grav_set_mass(self.h, len(m), _lib.f64(m)))

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-enrich", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (scaling sweeps at N=1e6)")
+    ap.add_argument("--dist-mode", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory exchange or NCCL all-gather")
     ap.add_argument("--step-mode", type=int, default=1, choices=[0, 1], help="1 GPU: 1 = persistent loop kernel, 0 = CUDA graph")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     return ap.parse_args()
@@ -241,7 +242,7 @@ def main():
     ctx.set_step_mode(args.step_mode)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        pkg.dist.init_context(ctx, rank, world, device="cuda")
+        pkg.dist.init_context(ctx, rank, world, device="cuda", mode=args.dist_mode)
 
     def barrier():
         if world > 1:
@@ -348,7 +349,9 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"N={n} Plummer, Maschberger IMF, r_vir=1 pc, Hermite-4 block timesteps, eta=0.14, eps2=0 "
                                    f"(BASELINE config 3); step = evolve_model(t + {args.dt_myr} Myr = {span:.5f} N-body)",
-                       "outer_dt_myr": args.dt_myr, "parallelism": f"i-partition x{world} + NCCL j all-gather" if world > 1 else "1 GPU",
+                       "outer_dt_myr": args.dt_myr, "parallelism": ("1 GPU" if world == 1 else
+                                       f"x{world}: replicated state, owner-computes (i % {world}), corrected particles scattered to peers over NVLink inside the loop kernel"
+                                       if args.dist_mode == "p2p" else f"i-partition x{world} + NCCL j all-gather"),
                        "l2": "256 MiB device write between timed steps (state is 20 MB < L2; kernel is FP64-bound)"},
             "block_steps_per_step": tot_steps / args.steps, "pairs_per_step": tot_pairs / args.steps,
             "wall_s_timed_region": wall, "dE_over_E": de, "t_end_nbody": t_now,

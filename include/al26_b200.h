@@ -61,6 +61,16 @@ int al26_device_info(al26_ctx *ctx, int *sm_count, int *clock_khz, int64_t *free
  * the reference's worker (al26_nbody.py:57,1711-1720). */
 int al26_dist_unique_id(void *out128);
 int al26_dist_init(al26_ctx *ctx, int rank, int world, const void *nccl_unique_id);
+/* how ranks exchange data inside evolve (before commit).  1 (default): peer memory -- every rank holds the
+ * full state, corrects the active particles it owns (i % world == rank) and stores them straight into every
+ * rank's staging slab over NVLink from inside the persistent loop kernel; one cross-GPU flag barrier per
+ * block step, no NCCL in the loop.  0: contiguous i-slices, NCCL all-gather of the predicted j-set + an
+ * 8-byte min-reduce per block step. */
+int al26_dist_set_mode(al26_ctx *ctx, int mode);
+/* peer-memory mode, after every al26_grav_commit: export this rank's slab as a 64-byte CUDA IPC handle, let
+ * the host all-gather the handles (torch.distributed), import the world x 64 bytes */
+int al26_dist_p2p_export(al26_ctx *ctx, void *out64);
+int al26_dist_p2p_import(al26_ctx *ctx, const void *handles, int world);
 
 /* ---- gravity -------------------------------------------------------------------------*/
 /* replaces: `gravity.parameters.epsilon_squared / timestep_parameter` (never set by the

@@ -14,7 +14,8 @@ from oracle import hermite as H
 from oracle import enrich_oracle as eo
 
 ctx = pkg.Context(local)
-pkg.dist.init_context(ctx, rank, world, device="cuda")
+MODE = os.environ.get("AL26_DIST_MODE", "p2p")
+pkg.dist.init_context(ctx, rank, world, device="cuda", mode=MODE)
 
 n = 4096
 c = pkg.ic.cluster(n, seed=7)
@@ -54,7 +55,7 @@ for k in range(1, 4):
 inv, fin, al, kk = e.get()
 assert np.array_equal(inv[:, i0:i1], st.inv[:, i0:i1]) and np.array_equal(fin[:, i0:i1], st.fin[:, i0:i1])
 assert np.array_equal(al[i0:i1], st.disk_alive[i0:i1]) and np.array_equal(kk, st.kicked)
-print(f"rank {rank}/{world}: PASS  acc err {err:.2e}, evolve steps {sg[0]} (oracle {so[0]}), pairs local {sg[1]} total {int(tot_pairs.item())}, dx {dx:.2e}", flush=True)
+print(f"[{MODE}] rank {rank}/{world}: PASS  acc err {err:.2e}, evolve steps {sg[0]} (oracle {so[0]}), pairs local {sg[1]} total {int(tot_pairs.item())}, dx {dx:.2e}", flush=True)
 dist.barrier()
 ctx.close()
 dist.destroy_process_group()
