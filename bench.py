@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=100_000)  # use --particles under torchrun (argparse prefix clash with --nnodes)
     ap.add_argument("--dt-myr", type=float, default=0.01)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-enrich", action="store_true")
