@@ -62,6 +62,7 @@ SIGNATURES = {
     "al26_grav_dbg_finish": (C.c_int, [_VP]),
     "al26_grav_force": (C.c_int, [_VP, C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32] + [_D] * 7),
     "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
+    "al26_enrich_last_kernel_ms": (C.c_int, [_VP, _PD]),
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
     "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),

@@ -69,7 +69,8 @@ struct al26_ctx {
   int sm_count = 0;
   int clock_khz = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  double last_kernel_ms = 0.0;  // kernels only (no host<->device copies) of the last al26_enrich_step
   std::string err;
   double last_ms = 0.0;
   int64_t last_launches = 0;
@@ -487,6 +488,7 @@ al26_ctx *al26_create(int device_id) {
   bool ok = cudaSetDevice(device_id) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
+            cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
             cudaMallocHost(&c->h_hdr, sizeof(GravHeader)) == cudaSuccess &&
             cudaMallocHost(&c->h_small, 16 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&c->h_events, (8 + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
@@ -518,6 +520,8 @@ void al26_destroy(al26_ctx *c) {
   if (c->h_events) cudaFreeHost(c->h_events);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev3) cudaEventDestroy(c->ev3);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1071,6 +1075,12 @@ int al26_last_device_ms(al26_ctx *c, double *ms, int64_t *kernel_launches) {
   return 0;
 }
 
+int al26_enrich_last_kernel_ms(al26_ctx *c, double *ms) {
+  if (!c || !ms) return AL26_EINVAL;
+  *ms = c->last_kernel_ms;
+  return 0;
+}
+
 int al26_grav_bench_force_n(al26_ctx *c, int64_t n_act, int reps, double *avg_ms, int64_t *pairs_per_eval) {
   if (!c) return AL26_EINVAL;
   if (!c->committed) return fail(c, AL26_ESTATE, "bench_force before commit");
@@ -1279,7 +1289,9 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
   p.q_local = q;
   p.decay26 = decay26; p.decay60 = decay60; p.with_agb = with_agb;
   CU(cudaMemsetAsync(e.counters, 0, 8 * sizeof(int), c->stream));
+  CU(cudaEventRecord(c->ev2, c->stream));
   c->launches += launch_enrich(e, p, c->stream);
+  CU(cudaEventRecord(c->ev3, c->stream));
   CU(cudaMemcpyAsync(c->h_events, e.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_events + 8, e.sn_events, ENR_MAX_SOURCES * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev1, c->stream));
@@ -1288,6 +1300,8 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+  c->last_kernel_ms = ms;
   c->last_launches = c->launches - l0;
   if (c->h_events[2]) return fail(c, AL26_ECAP, "more than %d massive stars", ENR_MAX_SOURCES);
   const int ne = c->h_events[1];

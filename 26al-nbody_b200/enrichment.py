@@ -87,5 +87,11 @@ class EnrichCore:
     def last_device_ms(self):
         return self.ctx.last_device_ms()
 
+    def last_kernel_ms(self):
+        """device time of the three enrichment kernels of the last step (copies excluded)"""
+        ms = C.c_double(0)
+        self.ctx.chk(self.L.al26_enrich_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         self.ctx.close()

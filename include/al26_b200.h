@@ -122,6 +122,9 @@ int al26_grav_force(al26_ctx *ctx, int64_t n, double eps2, const double *m, cons
 /* timing hook for bench.py: device time (ms) of the last al26_grav_evolve / al26_enrich_step,
  * measured with CUDA events on the library's own stream, and kernels launched in it */
 int al26_last_device_ms(al26_ctx *ctx, double *ms, int64_t *kernel_launches);
+/* bench hook: device time (ms) of the three enrichment kernels alone in the last al26_enrich_step
+ * (CUDA events around the kernels; host<->device copies excluded) */
+int al26_enrich_last_kernel_ms(al26_ctx *ctx, double *ms);
 /* bench hook: time `reps` full force evaluations (all i x all j, K1 only) on the committed
  * state with CUDA events on the library stream; returns average ms per evaluation */
 int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pairs_per_eval);
