@@ -256,13 +256,11 @@ class B200Gravity:
     (torch.distributed), so inside one process the worker count is the process's world size.
     """
 
-    def __init__(self, converter, number_of_workers=1, device=0, dist=None, **_ignored):
+    def __init__(self, converter, number_of_workers=1, device=0, ctx=None, **_ignored):
         self.converter = converter
         self._len_si = converter.length_si
-        ctx = _lib.Context(device)
-        if dist is not None:
-            ctx.dist_init(dist["rank"], dist["world"], dist["unique_id"])
-        self._core = GravityCore(ctx=ctx)
+        # multi-GPU: pass a Context already joined to the job (dist.init_context); one process per GPU
+        self._core = GravityCore(ctx=ctx if ctx is not None else _lib.Context(device))
         self._cache = None
         self.particles = _GravityParticles(self)
         self.parameters = _Parameters(self)
