@@ -66,6 +66,7 @@ SIGNATURES = {
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
     "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),
+    "al26_set_big_block": (C.c_int, [_VP, C.c_int]),
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     "al26_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
     "al26_enrich_step": (C.c_int, [_VP, C.c_int64, _D, _D, _VP] + [C.c_double] * 6 + [C.c_int, _I32, C.c_int64, _PI64]),
+    "al26_enrich_interloper": (C.c_int, [_VP, C.c_int64, _D, _D, _D, C.c_int64] + [C.c_double] * 6),
+    "al26_enrich_get_agb_raw": (C.c_int, [_VP, C.c_int64, _D]),
     "al26_enrich_get": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP]),
 }
 
@@ -171,6 +174,9 @@ class Context:
 
     def set_force_variant(self, v):
         self.chk(self.L.al26_set_force_variant(self.h, int(v)))
+
+    def set_big_block(self, n_act_min):
+        self.chk(self.L.al26_set_big_block(self.h, int(n_act_min)))
 
     def set_step_mode(self, mode):
         self.chk(self.L.al26_set_step_mode(self.h, int(mode)))

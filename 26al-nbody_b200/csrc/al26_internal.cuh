@@ -85,6 +85,7 @@ struct GravDev {
   int variant;    // force-kernel configuration (hermite_force.cu)
   int force_ipt;  // its i-particles per lane for big blocks
   const int *decomp_tab;  // n_jsplit by number of i-tiles (fill_decomp_table)
+  int big_nact;           // blocks of at least this many particles use force_ipt i-particles per lane
   double eps2, eta, dt_max, dt_min;
   double4 *pos, *vel, *acc, *jrk;
   double *t, *dt;
@@ -108,7 +109,7 @@ constexpr int FORCE_STAGES = 3;
 constexpr int FORCE_MIN_JCHUNK = 64;
 constexpr int FORCE_MAX_ROUNDS = 16;             // work items per CTA at most (load balance for big blocks)
 constexpr double FORCE_ITEM_OVERHEAD_PAIRS = 3200.0;  // fixed cost of one item (TMA prologue, barriers, reduction) in pair units
-constexpr int FORCE_BIG_NACT_PER_IPT = 1024;      // n_act >= this x IPT: IPT i-particles per lane
+constexpr int FORCE_BIG_NACT_DEFAULT = 2048;      // n_act >= GravDev::big_nact: the configuration's IPT i-particles per lane
 constexpr int FORCE_SPLIT_MAX_NACT = 16;         // n_act <= this: lanes split over j as well (tiny blocks)
 constexpr int FORCE_IPT_MAX = 4;
 
@@ -150,24 +151,24 @@ inline int choose_jsplit(int n_itiles, int ti, int n_tot, int grid) {
 }
 
 // table layout: entries [0, n_small) for ipt = 1 (index n_itiles - 1), then entries for ipt = ipt_big
-inline int decomp_small_entries(int ipt_big) { return (FORCE_BIG_NACT_PER_IPT * ipt_big + 31) / 32 + 1; }
-inline int decomp_table_entries(int n_loc, int ipt_big) {
-  return decomp_small_entries(ipt_big) + (n_loc + 32 * ipt_big - 1) / (32 * ipt_big) + 2;
+inline int decomp_small_entries(int big_nact) { return (big_nact + 31) / 32 + 1; }
+inline int decomp_table_entries(int n_loc, int ipt_big, int big_nact) {
+  return decomp_small_entries(big_nact) + (n_loc + 32 * ipt_big - 1) / (32 * ipt_big) + 2;
 }
-inline void fill_decomp_table(int *tab, int n_loc, int n_tot, int grid, int ipt_big) {
-  const int ns_small = decomp_small_entries(ipt_big);
+inline void fill_decomp_table(int *tab, int n_loc, int n_tot, int grid, int ipt_big, int big_nact) {
+  const int ns_small = decomp_small_entries(big_nact);
   for (int t = 1; t <= ns_small; t++) tab[t - 1] = choose_jsplit(t, 32, n_tot, grid);
-  const int nb = decomp_table_entries(n_loc, ipt_big) - ns_small;
+  const int nb = decomp_table_entries(n_loc, ipt_big, big_nact) - ns_small;
   for (int t = 1; t <= nb; t++) tab[ns_small + t - 1] = choose_jsplit(t, 32 * ipt_big, n_tot, grid);
 }
 
-__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, const int *__restrict__ tab, int ipt_big) {
+__host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, const int *__restrict__ tab, int ipt_big, int big_nact) {
   Decomp d;
-  d.ipt = (n_act >= FORCE_BIG_NACT_PER_IPT * ipt_big) ? ipt_big : 1;
+  d.ipt = (n_act >= big_nact) ? ipt_big : 1;
   d.ti = 32 * d.ipt;
   d.n_itiles = (n_act + d.ti - 1) / d.ti;
   if (d.n_itiles < 1) d.n_itiles = 1;
-  const int small = (FORCE_BIG_NACT_PER_IPT * ipt_big + 31) / 32 + 1;
+  const int small = (big_nact + 31) / 32 + 1;
   const int ns = tab[(d.ipt == 1 ? 0 : small) + d.n_itiles - 1];
   int jc = (n_tot + ns - 1) / ns;
   jc = (jc + 7) & ~7;
@@ -246,5 +247,16 @@ struct EnrichParams {
   int with_agb;
 };
 int launch_enrich(const EnrichDev &e, const EnrichParams &p, cudaStream_t s);
+
+// AGB interloper deposit (al26_nbody.py:985-1028, calc_intersection :1156-1190)
+struct InterloperParams {
+  int k_int;                 // global index of the interloper
+  const double *old_pc, *new_pc;  // [3][n_tot] positions before / after the gravity step, in pc
+  double q_test;             // largest d^2 with sqrt(d^2) <= r_test (pc^2)
+  double r_bub3;             // interloper_bubble_radius cubed (km^3)
+  double km_per_pc, rate26, rate60, dt_s;
+  double *raw;               // [2][n_loc] mass_{26al,60fe}_agb_raw
+};
+int launch_interloper(const EnrichDev &e, const InterloperParams &p, cudaStream_t s);
 
 }  // namespace al26

@@ -92,6 +92,7 @@ struct al26_ctx {
   int64_t n_tot = 0;
   int dbg_phase = 0;
   int force_variant = 0;
+  int big_nact = FORCE_BIG_NACT_DEFAULT;  // tuning: block size from which the force kernel holds several i per lane
   int step_mode = 1;      // 1: persistent cooperative loop kernel (1 GPU), 0: CUDA graph of 3 kernels per block step
   bool coop_ok = false;   // device supports cooperative launch
   cudaGraphExec_t graph = nullptr;
@@ -674,8 +675,9 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   CU(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
   CU(cudaMalloc(&g.hdr, sizeof(GravHeader)));
   {
-    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt));
-    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt);
+    g.big_nact = c->big_nact;
+    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt, g.big_nact));
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact);
     int *d_tab = nullptr;
     CU(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
     CU(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1036,8 +1038,9 @@ int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const 
   TRY(cudaMalloc(&g.hdr, sizeof(GravHeader)));
   int *d_tab = nullptr;
   {
-    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt));
-    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt);
+    g.big_nact = c->big_nact;
+    std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt, g.big_nact));
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact);
     TRY(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
     TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     g.decomp_tab = d_tab;
@@ -1125,6 +1128,14 @@ int al26_set_force_variant(al26_ctx *c, int variant) {
   return 0;
 }
 
+int al26_set_big_block(al26_ctx *c, int n_act_min) {
+  if (!c) return AL26_EINVAL;
+  if (n_act_min < 33 || n_act_min > (1 << 20)) return fail(c, AL26_EINVAL, "big-block threshold %d out of range", n_act_min);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_big_block during evolve");
+  c->big_nact = n_act_min;  // takes effect at the next commit
+  return 0;
+}
+
 int al26_set_step_mode(al26_ctx *c, int mode) {
   if (!c) return AL26_EINVAL;
   if (mode != 0 && mode != 1) return fail(c, AL26_EINVAL, "step mode must be 0 (graph) or 1 (persistent loop)");
@@ -1193,7 +1204,7 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   slice_of(n, c->rank, c->world, d0, nloc);
   const size_t nt = (size_t)n, nl = (size_t)nloc;
   CU(cudaMalloc(&c->e_glob, 12 * nt * sizeof(double)));
-  CU(cudaMalloc(&c->e_loc, 18 * nl * sizeof(double)));
+  CU(cudaMalloc(&c->e_loc, 20 * nl * sizeof(double)));  // r_disk, tau, inv[8], fin[8], agb_raw[2]
   CU(cudaMalloc(&c->e_flags, nt + nl));
   CU(cudaMalloc(&c->e_ints, (8 + 2 * ENR_MAX_SOURCES) * sizeof(int)));
   CU(cudaMalloc(&c->e_src, 2 * ENR_MAX_SOURCES * sizeof(double4)));
@@ -1214,7 +1225,7 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   CU(cudaMemcpyAsync(G + 11 * nt, sn60, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(Lc, r_disk_km + d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(Lc + nl, tau_disk_myr + d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(Lc + 2 * nl, 0, 16 * nl * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(Lc + 2 * nl, 0, 18 * nl * sizeof(double), c->stream));
   CU(cudaMemcpyAsync(c->e_flags, kicked, nt, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->e_flags + nt, disk_alive + d0, nl, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1310,6 +1321,50 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
     if (!sn_events || sn_cap < ne) return fail(c, AL26_ECAP, "%d supernova events exceed sn_cap %lld", ne, (long long)sn_cap);
     memcpy(sn_events, c->h_events + 8, (size_t)ne * sizeof(int));
   }
+  return 0;
+}
+
+int al26_enrich_interloper(al26_ctx *c, int64_t n, const double *mass_msun, const double *pos_old_pc,
+                           const double *pos_new_pc, int64_t interloper_index, double r_test_pc, double r_bub_km,
+                           double km_per_pc, double rate26_kg_s, double rate60_kg_s, double dt_s) {
+  if (!c) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_interloper before enrich_commit");
+  if (n != c->e.n_tot || !mass_msun || !pos_old_pc || !pos_new_pc) return fail(c, AL26_EINVAL, "enrich_interloper: size mismatch or null array");
+  if (interloper_index < 0 || interloper_index >= n) return fail(c, AL26_EINVAL, "interloper index out of range");
+  if (!(r_test_pc > 0.0) || !(r_bub_km > 0.0) || !(km_per_pc > 0.0)) return fail(c, AL26_EINVAL, "radii must be positive");
+  CU(cudaSetDevice(c->device));
+  const size_t nt = (size_t)n, nl = (size_t)c->e.n_loc;
+  double *G = c->e_glob;
+  CU(cudaMemcpyAsync(G, mass_msun, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + 2 * nt, pos_old_pc, 3 * nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(G + 5 * nt, pos_new_pc, 3 * nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  InterloperParams p;
+  p.k_int = (int)interloper_index;
+  p.old_pc = G + 2 * nt;
+  p.new_pc = G + 5 * nt;
+  // largest q with sqrt(q) <= r: `sqrt(d2) <= r` <=> `d2 <= q`
+  double q = r_test_pc * r_test_pc;
+  while (sqrt(q) > r_test_pc) q = nextafter(q, -INFINITY);
+  while (sqrt(nextafter(q, INFINITY)) <= r_test_pc) q = nextafter(q, INFINITY);
+  p.q_test = q;
+  p.r_bub3 = r_bub_km * (r_bub_km * r_bub_km);
+  p.km_per_pc = km_per_pc; p.rate26 = rate26_kg_s; p.rate60 = rate60_kg_s; p.dt_s = dt_s;
+  p.raw = c->e_loc + 18 * nl;
+  c->launches += launch_interloper(c->e, p, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int al26_enrich_get_agb_raw(al26_ctx *c, int64_t n, double *raw) {
+  if (!c || !raw) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_get_agb_raw before enrich_commit");
+  if (n != c->e.n_tot) return fail(c, AL26_EINVAL, "size mismatch");
+  CU(cudaSetDevice(c->device));
+  const size_t nl = (size_t)c->e.n_loc;
+  for (int r = 0; r < 2; r++)
+    CU(cudaMemcpyAsync(raw + (size_t)r * n + c->e.d0, c->e_loc + (18 + r) * nl, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -196,6 +196,61 @@ __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const 
   }
 }
 
+// AGB interloper deposit (al26_nbody.py:985-1028): per disc, the fraction of the step spent within r_test of
+// the interloper, by the reference's own recipe -- 1024 np.linspace samples of both straight-line paths
+// (calc_intersection, :1156-1190; linspace = k*step + start with step = (stop-start)/1023, last = stop) --
+// then the sweep-up deposit onto the agb rows.  The interloper's samples are shared by the CTA.
+constexpr int ISECT_N = 1024;
+
+__global__ void __launch_bounds__(EN_T) k_enrich_interloper(const EnrichDev e, const InterloperParams p) {
+  __shared__ double s1[3][ISECT_N];
+  const size_t nt = (size_t)e.n_tot;
+  for (int c = 0; c < 3; c++) {
+    const double a = p.old_pc[c * nt + p.k_int], b = p.new_pc[c * nt + p.k_int];
+    const double step = (b - a) / (double)(ISECT_N - 1);
+    for (int k = threadIdx.x; k < ISECT_N; k += EN_T) s1[c][k] = (k == ISECT_N - 1) ? b : ((double)k * step + a);
+  }
+  __syncthreads();
+  const int li = blockIdx.x * EN_T + threadIdx.x;
+  if (li >= e.n_loc) return;
+  const int gi = e.d0 + li;
+  const double m = e.mass_msun[gi];
+  if (!((m >= 0.1) && (m <= 3.0)) || gi == p.k_int) return;  // for i in lm_id: if not is_interloper (:990-991)
+  const double xo = p.old_pc[gi], yo = p.old_pc[nt + gi], zo = p.old_pc[2 * nt + gi];
+  const double xn = p.new_pc[gi], yn = p.new_pc[nt + gi], zn = p.new_pc[2 * nt + gi];
+  const double sx = (xn - xo) / (double)(ISECT_N - 1), sy = (yn - yo) / (double)(ISECT_N - 1),
+               sz = (zn - zo) / (double)(ISECT_N - 1);
+  int cnt = 0;
+#pragma unroll 4
+  for (int k = 0; k < ISECT_N - 1; k++) {
+    const double kk = (double)k;
+    const double dx = s1[0][k] - (kk * sx + xo), dy = s1[1][k] - (kk * sy + yo), dz = s1[2][k] - (kk * sz + zo);
+    cnt += (dx * dx + dy * dy + dz * dz <= p.q_test) ? 1 : 0;
+  }
+  {
+    const double dx = s1[0][ISECT_N - 1] - xn, dy = s1[1][ISECT_N - 1] - yn, dz = s1[2][ISECT_N - 1] - zn;
+    cnt += (dx * dx + dy * dy + dz * dz <= p.q_test) ? 1 : 0;
+  }
+  if (cnt == 0) return;                                                   // if intersection_frac != 0.0 (:1015)
+  const double frac = (double)cnt / (double)ISECT_N;
+  const double ex = (xn - xo) * p.km_per_pc, ey = (yn - yo) * p.km_per_pc, ez = (zn - zo) * p.km_per_pc;
+  double trav = sqrt(ex * ex + ey * ey + ez * ez);                        // :1020
+  trav *= frac;                                                           // :1021
+  const double rd = e.r_disk[li];
+  const double eta = 0.75 * (rd * rd) * trav / p.r_bub3;                  // :1022
+  const double a26 = p.rate26 * eta * p.dt_s, a60 = p.rate60 * eta * p.dt_s;  // :1023-1024
+  const size_t n = (size_t)e.n_loc;
+  e.inv[3 * n + li] += a26;                                               // mass_26al_agb (:1025)
+  e.inv[7 * n + li] += a60;                                               // mass_60fe_agb (:1026)
+  p.raw[li] += a26;                                                       // *_agb_raw (:1027-1028)
+  p.raw[n + li] += a60;
+}
+
+int launch_interloper(const EnrichDev &e, const InterloperParams &p, cudaStream_t s) {
+  k_enrich_interloper<<<(e.n_loc + EN_T - 1) / EN_T, EN_T, 0, s>>>(e, p);
+  return 1;
+}
+
 int launch_enrich(const EnrichDev &e, const EnrichParams &p, cudaStream_t s) {
   k_enrich_classify<<<(e.n_tot + EN_T - 1) / EN_T, EN_T, 0, s>>>(e);
   k_enrich_sources<<<1, 1024, 0, s>>>(e);

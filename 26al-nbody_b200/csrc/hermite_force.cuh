@@ -202,7 +202,7 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmemT<C> &sm, co
 template <class C>
 __device__ __forceinline__ void force_items(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *ctl, const int n_act,
                                             const int n_ctas, uint32_t &it) {
-  const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, C::IPT);
+  const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, C::IPT, g.big_nact);
   const int n_items = d.n_itiles * d.n_jsplit;
   const int tid = threadIdx.x;
   while (true) {

@@ -241,7 +241,7 @@ template <int MODE, bool DIST>
 __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, const int n_act, const double tn,
                                               const int block_id, const int n_blocks, unsigned long long *sh,
                                               double (*shr)[7], const unsigned long long step_id = 0) {
-  const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt);
+  const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt, g.big_nact);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   unsigned long long c_bits = INF_BITS;

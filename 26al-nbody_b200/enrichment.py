@@ -75,6 +75,21 @@ class EnrichCore:
             self._sn, len(self._sn), C.byref(ne)))
         return self._sn[: ne.value].copy()
 
+    def interloper(self, mass_msun, pos_old_pc, pos_new_pc, interloper_index, r_bub_km, rate26_kg_s, rate60_kg_s, dt_s,
+                   r_test_pc=0.1, km_per_pc=3.08567758128e13):
+        """AGB interloper deposit (al26_nbody.py:985-1028); call before step(..., with_agb=True)."""
+        po, pn = _lib.f64(pos_old_pc), _lib.f64(pos_new_pc)
+        if po.shape != (3, self.n) or pn.shape != (3, self.n):
+            raise ValueError(f"positions must have shape (3, {self.n})")
+        self.ctx.chk(self.L.al26_enrich_interloper(self.h, self.n, _lib.f64(mass_msun), po, pn, int(interloper_index),
+                                                   float(r_test_pc), float(r_bub_km), float(km_per_pc),
+                                                   float(rate26_kg_s), float(rate60_kg_s), float(dt_s)))
+
+    def get_agb_raw(self):
+        raw = np.zeros((2, self.n))
+        self.ctx.chk(self.L.al26_enrich_get_agb_raw(self.h, self.n, raw))
+        return raw
+
     def get(self, want_inv=True, want_fin=True):
         inv = np.zeros((NINV, self.n)) if want_inv else None
         fin = np.zeros((NINV, self.n)) if want_fin else None

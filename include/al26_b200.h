@@ -134,6 +134,9 @@ int al26_grav_bench_force_n(al26_ctx *ctx, int64_t n_act, int reps, double *avg_
 /* tuning hook: pick one of the compiled force-kernel configurations (0 = default); applies at the
  * next al26_grav_commit */
 int al26_set_force_variant(al26_ctx *ctx, int variant);
+/* tuning hook: active blocks of at least n_act_min particles use the configuration's several i-particles
+ * per lane (default 2048); applies at the next al26_grav_commit */
+int al26_set_big_block(al26_ctx *ctx, int n_act_min);
 /* tuning hook: how block steps are driven on one GPU.  1 (default): one persistent cooperative kernel
  * runs the whole predict -> force -> correct loop with grid barriers; 0: a CUDA graph of three kernels
  * per block step (always used when world > 1, where NCCL calls sit between the kernels) */
@@ -174,6 +177,18 @@ int al26_enrich_step(al26_ctx *ctx, int64_t n, const double *mass_msun, const do
                      const double *pos_vel, double dt_s, double t_new_myr, double r_bub_local_km,
                      double r_bub_global_km, double decay26, double decay60, int with_agb,
                      int32_t *sn_events, int64_t sn_cap, int64_t *n_sn_events);
+/* replaces the AGB interloper deposit of al26_nbody.py:985-1028 (optional `-i` flag): per disc
+ * (0.1 <= mass_msun <= 3, not the interloper itself) the fraction of the step spent within r_test_pc of the
+ * interloper by calc_intersection's recipe (:1156-1190: 1024 np.linspace samples of both straight-line paths,
+ * positions in pc before / after the gravity step, [3][n] each), then
+ * rate * 0.75 r_disk^2 (|dx_disc| frac) / r_bub^3 * dt onto the agb rows and the never-decayed agb_raw
+ * accumulators.  The caller has already checked interloper_time > 0 and rate > 0 (:985,:989).  Call it BEFORE
+ * al26_enrich_step(..., with_agb = 1) of the same outer step (the reference deposits, then decays). */
+int al26_enrich_interloper(al26_ctx *ctx, int64_t n, const double *mass_msun, const double *pos_old_pc,
+                           const double *pos_new_pc, int64_t interloper_index, double r_test_pc, double r_bub_km,
+                           double km_per_pc, double rate26_kg_s, double rate60_kg_s, double dt_s);
+/* cluster.mass_{26al,60fe}_agb_raw (al26_nbody.py:1560,1572): raw[2][n] */
+int al26_enrich_get_agb_raw(al26_ctx *ctx, int64_t n, double *raw);
 /* replaces: reading cluster.mass_*_{local,global,sne,agb}[_final], disk_alive, kicked when
  * yields / checkpoints are written (al26_nbody.py:1097-1105).  Any pointer may be NULL. */
 int al26_enrich_get(al26_ctx *ctx, int64_t n, double *inv /*[8][n]*/, double *fin /*[8][n]*/,

@@ -157,6 +157,44 @@ def enrich_step(st, mass_msun, mdot, x, y, z, vx, vy, vz, dt_s, t_new_myr,
     return events
 
 
+def calc_intersection(x1o, y1o, z1o, x1n, y1n, z1n, x2o, y2o, z2o, x2n, y2n, z2n, r, n=1024):
+    """al26_nbody.py:1156-1190: fraction of n linspace samples of two straight-line paths closer than r."""
+    x1i, y1i, z1i = np.linspace(x1o, x1n, n), np.linspace(y1o, y1n, n), np.linspace(z1o, z1n, n)
+    x2i, y2i, z2i = np.linspace(x2o, x2n, n), np.linspace(y2o, y2n, n), np.linspace(z2o, z2n, n)
+    ri = ((x1i - x2i) ** 2 + (y1i - y2i) ** 2 + (z1i - z2i) ** 2) ** 0.5
+    return np.array(ri <= r).sum() / n
+
+
+def interloper_step(st, raw, mass_msun, is_interloper, pos_old_pc, pos_new_pc, rate26, rate60, dt, r_bub, km_per_pc,
+                    r_test_pc=0.1):
+    """AGB interloper deposit, al26_nbody.py:985-1028 (the caller has already established that
+    interloper_time > 0 and that a rate is positive).  pos_*_pc: (3, n) positions in pc before / after the
+    gravity step; rates in kg/s, dt in s, r_bub (interloper_bubble_radius) and r_disk in km.
+    `raw` is the (2, n) mass_{26al,60fe}_agb_raw accumulator (never decayed).  Returns the per-disc fractions."""
+    hm, lm = classify(mass_msun)
+    k = int(np.nonzero(is_interloper)[0][-1])
+    frac = np.zeros(len(mass_msun))
+    for i in lm:
+        if is_interloper[i]:
+            continue
+        f = calc_intersection(pos_old_pc[0, k], pos_old_pc[1, k], pos_old_pc[2, k], pos_new_pc[0, k], pos_new_pc[1, k],
+                              pos_new_pc[2, k], pos_old_pc[0, i], pos_old_pc[1, i], pos_old_pc[2, i], pos_new_pc[0, i],
+                              pos_new_pc[1, i], pos_new_pc[2, i], r_test_pc)
+        frac[i] = f
+        if f != 0.0:
+            dx = (pos_new_pc[:, i] - pos_old_pc[:, i]) * km_per_pc
+            d_disk_trav = np.sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2])
+            d_disk_trav *= f
+            eta_bub = 0.75 * (st.r_disk[i] * st.r_disk[i]) * d_disk_trav / (r_bub * (r_bub * r_bub))
+            a26 = rate26 * eta_bub * dt
+            a60 = rate60 * eta_bub * dt
+            st.inv[AGB26, i] += a26
+            st.inv[AGB60, i] += a60
+            raw[0, i] += a26
+            raw[1, i] += a60
+    return frac
+
+
 def sqrt_threshold(radius):
     """Smallest double q with sqrt(q) >= radius, so that `radius <= sqrt(d2)` <=> `d2 >= q`
     for every double d2 (sqrt is correctly rounded and monotone).  Test helper that

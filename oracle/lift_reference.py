@@ -95,6 +95,16 @@ def generate(out_path):
         out[f"{tag}_g60"] = cwa(*args, c["wr60"], c["rdisk"], 0.0, rvir, dt_s)
         out[f"{tag}_l26"] = cwa(*args, c["wr26"], c["rdisk"], float(c["bubble_km"]), float(c["bubble_km"]), dt_s)
         out[f"{tag}_l60"] = cwa(*args, c["wr60"], c["rdisk"], float(c["bubble_km"]), float(c["bubble_km"]), dt_s)
+    # calc_intersection (interloper path): seeded straight-line pairs, some grazing the 0.1 pc sphere
+    rng = np.random.default_rng(9)
+    m = 400
+    a_old = rng.normal(0, 1.0, (3,)); a_new = a_old + rng.normal(0, 0.3, (3,))
+    b_old = a_old[:, None] + rng.normal(0, 0.15, (3, m)); b_new = b_old + rng.normal(0, 0.2, (3, m))
+    b_new[:, :20] = b_old[:, :20]  # discs that do not move
+    fr = np.array([fns["calc_intersection"](a_old[0], a_old[1], a_old[2], a_new[0], a_new[1], a_new[2],
+                                            b_old[0, i], b_old[1, i], b_old[2, i], b_new[0, i], b_new[1, i], b_new[2, i], 0.1)
+                   for i in range(m)])
+    out["isect_a_old"], out["isect_a_new"], out["isect_b_old"], out["isect_b_new"], out["isect_frac"] = a_old, a_new, b_old, b_new, fr
     np.savez_compressed(out_path, **out)
     return out
 

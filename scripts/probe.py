@@ -6,6 +6,24 @@ pkg = importlib.import_module("26al-nbody_b200")
 ctx = pkg.Context(0)
 print("device", ctx.device_info())
 print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+if os.environ.get("PROBE_BIGBLOCK"):
+    n = 100000
+    c = pkg.ic.cluster(n, seed=0)
+    for thr in (2048, 1024, 512, 256, 128, 64):
+        ctx.set_big_block(thr)
+        g = pkg.GravityCore(ctx=ctx)
+        g.set_time(0.0)
+        g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+        row = []
+        for na, reps in ((64, 20), (100, 20), (200, 20), (300, 20), (500, 20), (800, 20), (1000, 20), (1500, 20), (2000, 20)):
+            ms, pairs = g.bench_force(reps, n_act=na)
+            row.append(f"{na}:{pairs/ms*1e-6:.0f}G")
+        t_end = 2.0 ** -5
+        steps, pairs = g.evolve(t_end)
+        ms, _ = g.last_device_ms()
+        print(f"big_block {thr}: " + " ".join(row) + f" | evolve 2^-5: {ms:.1f} ms, {pairs/ms*1e-6:.1f} G", flush=True)
+    ctx.set_big_block(2048)
+    sys.exit(0)
 if os.environ.get("PROBE_VARIANTS"):
     n = 100000
     c = pkg.ic.cluster(n, seed=0)

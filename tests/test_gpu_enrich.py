@@ -151,3 +151,36 @@ def test_full_size_properties_1e6(pkg, ctx):
     inv2 = e.get()[0]
     assert np.array_equal(inv2[R["global26"]], inv1[R["global26"]] * 0.5)
     assert np.array_equal(inv2[R["global60"]], inv1[R["global60"]] * 0.25)
+
+
+def test_interloper_vs_reference_golden_and_oracle(pkg, ctx, golden):
+    """AGB interloper: intersection fractions bit-exact against the reference's own
+    calc_intersection (golden from the lifted function), deposits bit-exact against the oracle."""
+    a0, a1, b0, b1, fr = (golden[k] for k in ("isect_a_old", "isect_a_new", "isect_b_old", "isect_b_new", "isect_frac"))
+    m = b0.shape[1]
+    n = m + 1                                  # the interloper is the last star (:974)
+    old = np.concatenate([b0, a0[:, None]], axis=1)
+    new = np.concatenate([b1, a1[:, None]], axis=1)
+    mass = np.full(n, 1.0); mass[5] = 8.0      # star 5 bears no disc
+    is_int = np.zeros(n, bool); is_int[-1] = True
+    rd = np.full(n, 1.49597870691e10)
+    e = pkg.EnrichCore(ctx=ctx)
+    e.commit(rd, np.full(n, 1e9), np.ones(n), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n))
+    st = eo.EnrichState(rd, np.full(n, 1e9), np.ones(n, bool), np.zeros(n, bool), *(np.zeros(n),) * 4)
+    raw = np.zeros((2, n))
+    kmpc, rbub, r26, r60, dt = 3.08567758128e13, 0.1 * 3.08567758128e13, 2.0e13, 3.0e10, 3.15e11
+    for rep in range(2):                       # two steps: deposits accumulate, raw is never decayed
+        e.interloper(mass, old, new, n - 1, rbub, r26, r60, dt)
+        frac = eo.interloper_step(st, raw, mass, is_int, old, new, r26, r60, dt, rbub, kmpc)
+        assert np.array_equal(frac[:m][mass[:m] == 1.0], fr[mass[:m] == 1.0])  # oracle == reference function
+        f26, f60 = 0.9, 0.95
+        e.step(mass, np.zeros(n), np.concatenate([new, np.zeros((3, n))]) * kmpc, dt, 0.01 * (rep + 1), 3e12, 3e13, f26, f60, with_agb=True)
+        eo.enrich_step(st, mass, np.zeros(n), *(new * kmpc), *np.zeros((3, n)), dt, 0.01 * (rep + 1), 3e12, 3e13, f26, f60, with_agb=True)
+    inv, fin, alive, kicked = e.get()
+    R = pkg.ROW
+    assert np.array_equal(inv, st.inv) and np.array_equal(fin, st.fin)
+    assert np.array_equal(e.get_agb_raw(), raw)
+    hit = (fr > 0) & np.any(b1 != b0, axis=0)  # a disc that does not move sweeps up nothing (d_disk_trav = 0)
+    hit[5] = False
+    assert np.array_equal(inv[R["agb26"]][:m] > 0, hit) and inv[R["agb26"]][-1] == 0.0 and raw[0, 5] == 0.0
+    assert np.all(raw[0][:m][hit] > inv[R["agb26"]][:m][hit])  # the inventory decays, raw does not

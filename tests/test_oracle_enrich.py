@@ -114,3 +114,11 @@ def test_enrich_step_semantics():
     assert np.array_equal(st.fin[eo.GLOBAL26, still], st.inv[eo.GLOBAL26, still])
     for i in lm[gone[lm]]:
         assert st.fin[eo.GLOBAL26, i] != st.inv[eo.GLOBAL26, i] or st.inv[eo.GLOBAL26, i] == 0
+
+
+def test_intersection_bit_exact_vs_reference_golden(golden):
+    """calc_intersection (al26_nbody.py:1156-1190): restatement == the reference's own function"""
+    a0, a1, b0, b1, fr = (golden[k] for k in ("isect_a_old", "isect_a_new", "isect_b_old", "isect_b_new", "isect_frac"))
+    mine = np.array([eo.calc_intersection(*a0, *a1, *b0[:, i], *b1[:, i], 0.1) for i in range(b0.shape[1])])
+    assert np.array_equal(mine, fr) and np.count_nonzero(fr) > 20
+    assert eo.calc_intersection(-1, 0, 0, 1, 0, 0, 0, 0.05, 0, 0, 0.05, 0, 0.1) == 0.0859375
