@@ -15,6 +15,7 @@ from . import ic  # noqa: F401
 from . import dist  # noqa: F401
 from . import stellar, driver  # noqa: F401
 from .stellar import StellarStub, YieldTables  # noqa: F401
+from .yields_io import Yields  # noqa: F401
 
 __all__ = ["units", "Al26Error", "Context", "Particles", "Channel", "GravityCore", "B200Gravity",
            "EnrichCore", "decay_fractions", "ic", "load", "dist_unique_id"]

@@ -3,8 +3,10 @@ in the phase order of /root/reference/al26_nbody.py:704-1113 / :1612-1766, with 
 B200: `gravity.evolve_model` (:833) and the disc routines (:878-1086).
 
 Not optimised host code: it exists so that BASELINE configs 1-2 run end to end through the drop-in
-boundary, with the reference's own phase timers (`grav / stel / winds+decay / step`, :796-1109).  What is
-NOT here (out of scope): checkpoints / yields files, the AGB interloper, plotting.
+boundary, with the reference's own phase timers (`grav / stel / winds+decay / step`, :796-1109), and
+optionally writes the reference's yields book / cluster-yields.csv (yields_io.py) on save steps.  What is NOT
+here (out of scope): state checkpoints (pickle), the AGB interloper's set-up and AGB wind
+tables (the deposit kernel itself is available: EnrichCore.interloper), plotting.
 
 Differences from the script that are deliberate and do not change results:
   * the virial radius (`cluster.virial_radius()`, an O(N^2) numpy sum every outer step, :770) comes from the
@@ -81,10 +83,13 @@ def pull_inventories(enrich, cluster):
         setattr(cluster, col + "_final", fin[ROW[row]] | U.kg)
     cluster.disk_alive = alive
     cluster.kicked = kicked
+    raw = enrich.get_agb_raw()
+    cluster.mass_26al_agb_raw = raw[0] | U.kg                                     # :1560,1572
+    cluster.mass_60fe_agb_raw = raw[1] | U.kg
 
 
 def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=False, verbose=False, log=print,
-                      sync_cluster=True):
+                      sync_cluster=True, yields=None):
     """One outer step (al26_nbody.py:704-1113).  Returns (finish, info)."""
     tm = {}
     t0 = time.perf_counter()
@@ -128,6 +133,8 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
     tm["discs"] = time.perf_counter() - t1
     if save:
         pull_inventories(enrich, cluster)
+        if yields is not None:
+            yields.update_state(gravity.model_time, cluster)                      # :1101
     tm["step"] = time.perf_counter() - t0
     if verbose:
         log("t = {:.3f} Myr: grav {:.3f} s, stel {:.3f} s, discs {:.3f} s, step {:.3f} s".format(
@@ -138,7 +145,7 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
 
 
 def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, max_outer_steps=None, verbose=False,
-        device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print):
+        device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None):
     """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200"."""
     from .gravity import B200Gravity
     stellar = stellar or StellarStub()
@@ -151,10 +158,16 @@ def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, m
     history = []
     n_iter = 0
     finish = False
+    ybook = None
+    if yields_file is not None:                                                   # Yields(filename) + first state (:1741)
+        from .yields_io import Yields
+        ybook = Yields(yields_file)
+        pull_inventories(enrich, cluster)
+        ybook.update_state(gravity.model_time, cluster)
     while not finish:                                                             # :1754-1760
         save = (n_iter % 10 == 0)
         finish, info = evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=save,
-                                         verbose=verbose, log=log)
+                                         verbose=verbose, log=log, yields=ybook)
         history.append(info)
         n_iter += 1
         if max_outer_steps is not None and n_iter >= max_outer_steps:

@@ -68,3 +68,33 @@ def test_init_cluster_columns(pkg):
     assert abs(np.mean(x)) < 0.2 and 0.3 < np.std(x) < 2.0
     with pytest.raises(ValueError):
         pkg.driver.init_cluster("king", 10, 1.0 | U.pc)
+
+
+def test_yields_book_and_csv_format(pkg, tmp_path):
+    """the reference's cluster-yields.csv format and Yields dict keys (al26_nbody.py:125-264)"""
+    U = pkg.units
+    cl = pkg.Particles(3)
+    kg = U.MSUN_KG
+    cl.mass_26al_local = np.array([1.0, 2.0, 3.0]) * 1e-9 * kg | U.kg
+    cl.mass_26al_global = np.array([1.0, 1.0, 1.0]) * 1e-10 * kg | U.kg
+    cl.mass_26al_sne = np.zeros(3) | U.kg
+    cl.mass_60fe_local = np.array([4.0, 0.0, 0.0]) * 1e-12 * kg | U.kg
+    cl.mass_60fe_global = np.zeros(3) | U.kg
+    cl.mass_60fe_sne = np.array([0.0, 5.0, 0.0]) * 1e-11 * kg | U.kg
+    cl.mass_26al_local_final = cl.mass_26al_local
+    base = str(tmp_path / "run")
+    y = pkg.Yields(base)
+    y.update_state(0.0 | U.Myr, cl)
+    cl.mass_26al_local = np.array([2.0, 2.0, 3.0]) * 1e-9 * kg | U.kg
+    y.update_state(0.1 | U.Myr, cl)
+    lines = open(base + "-cluster-yields.csv").read().splitlines()
+    assert lines[0] == "time,local_26al,global_26al,sne_26al,local_60fe,global_60fe,sne_60fe"
+    assert lines[1] == "0.000000e+00,6.000000e-09,3.000000e-10,0.000000e+00,4.000000e-12,0.000000e+00,5.000000e-11"
+    assert lines[2].startswith("1.000000e-01,7.000000e-09,") and len(lines) == 3
+    assert y.time == [0.0, 0.1] and len(y.local_26al) == 2 and y.agb_26al[0] == [0.0, 0.0, 0.0]
+    assert y.local_26al_final == pytest.approx([1e-9, 2e-9, 3e-9]) or y.local_26al_final == pytest.approx([2e-9, 2e-9, 3e-9])
+    path = y.marinate(base + "-yields")
+    z = pkg.Yields(base)
+    z.plate(path)
+    assert z.time == y.time and z.sum_local_26al == pytest.approx(y.sum_local_26al) and z.first_write is False
+    assert np.allclose(z.local_26al, y.local_26al)
