@@ -145,13 +145,25 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
 
 
 def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, max_outer_steps=None, verbose=False,
-        device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None):
+        device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None,
+        epsilon=None, progress=None):
     """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200"."""
     from .gravity import B200Gravity
+    from .gravity import GravityCore
+    from . import _lib
     stellar = stellar or StellarStub()
+    ctx = _lib.Context(device)
+    pot = None
+    if model == "fractal" and nstars > 2000:
+        def pot(m, x, y, z):  # the fractal generator's virial scaling needs U: use the device pair reduction
+            g0 = GravityCore(ctx=ctx)
+            g0.commit(m, x, y, z, np.zeros_like(x), np.zeros_like(x), np.zeros_like(x))
+            return g0.energies()[1]
     cluster, converter = init_cluster(model, nstars, Rc, yields=yields, stellar=stellar, seed=seed,
-                                      fractal_dimension=fractal_dimension)
-    gravity = B200Gravity(converter, device=device)
+                                      fractal_dimension=fractal_dimension, potential_energy=pot)
+    gravity = B200Gravity(converter, ctx=ctx)
+    if epsilon is not None:  # the script never sets it (ph4 default 0); sub-virial fractals need it, see DESIGN.md
+        gravity.parameters.epsilon_squared = epsilon * epsilon
     gravity.particles.add_particles(cluster)                                      # :1728
     stellar.particles.add_particles(cluster)                                      # :1731
     enrich = make_enrichment(gravity, cluster, converter)
@@ -169,6 +181,8 @@ def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, m
         finish, info = evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=save,
                                          verbose=verbose, log=log, yields=ybook)
         history.append(info)
+        if progress is not None:
+            progress(n_iter, info)
         n_iter += 1
         if max_outer_steps is not None and n_iter >= max_outer_steps:
             break

@@ -224,3 +224,25 @@ def test_full_size_properties_1e5(pkg, grav):
     assert np.all(t == 0.0) and np.all(np.log2(dt) == np.round(np.log2(dt)))
     k1, u1, _ = grav.energies()
     assert abs((k1 + u1) - (k + u)) / abs(k + u) < 1e-8
+
+
+def test_full_size_properties_1e6(pkg, ctx):
+    """BASELINE config 4 size (N = 1e6): one full force evaluation, size-independent checks."""
+    n = 1_000_000
+    c = pkg.ic.cluster(n, seed=7, require_massive=False)
+    p = [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
+    ctx.set_step_mode(1)
+    g = pkg.GravityCore(ctx=ctx)
+    g.set_time(0.0)
+    g.commit(*p)
+    g.initialize()
+    a = g.get_acc_jerk()
+    m = p[0]
+    for comps in (a[:3], a[3:6]):
+        v = m * np.stack(comps)
+        assert np.max(np.abs(v.sum(axis=1))) < 1e-11 * np.abs(v).sum()  # sum m a = sum m jerk = 0
+    idx = np.sort(np.random.default_rng(1).choice(n, 48, replace=False)).astype(np.int32)
+    ref = H.force(*p, idx=idx, long_double=True)
+    assert vec_rel([c_[idx] for c_ in a[:3]], ref[:3]) < TOL and vec_rel([c_[idx] for c_ in a[3:6]], ref[3:6]) < TOL
+    t, dt = g.get_timesteps()
+    assert np.all(np.log2(dt) == np.round(np.log2(dt))) and dt.max() <= 2.0 ** -5
