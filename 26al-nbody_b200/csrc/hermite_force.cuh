@@ -205,16 +205,21 @@ __device__ __forceinline__ void force_items(const GravDev &g, ForceSmemT<C> &sm,
   const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, C::IPT, g.big_nact);
   const int n_items = d.n_itiles * d.n_jsplit;
   const int tid = threadIdx.x;
-  while (true) {
-    __syncthreads();
-    if (tid == 0) sm.item = atomicAdd(&ctl->work_counter, 1);
-    __syncthreads();
-    const int item = sm.item;
-    if (item >= n_items) break;
+  // first round: CTA b takes item b with no atomic; later rounds (only when there are more items than CTAs)
+  // draw from the shared counter, which therefore counts items n_ctas, n_ctas + 1, ...  Small blocks -- one
+  // round -- pay no atomic round trip at all.
+  int item = blockIdx.x;
+  while (item < n_items) {
     if (d.ipt > 1) run_item<C, C::IPT, false>(g, sm, d, n_act, item, it);
     else if (n_act <= FORCE_SPLIT_MAX_NACT) run_item<C, 1, true>(g, sm, d, n_act, item, it);
     else run_item<C, 1, false>(g, sm, d, n_act, item, it);
+    if (n_items <= n_ctas) break;
+    __syncthreads();
+    if (tid == 0) sm.item = n_ctas + atomicAdd(&ctl->work_counter, 1);
+    __syncthreads();
+    item = sm.item;
   }
+  __syncthreads();  // red[] / stage buffers are free again for whoever runs next in this CTA
 }
 
 template <class C>

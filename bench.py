@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (scaling sweeps at N=1e6)")
     ap.add_argument("--dist-mode", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory exchange or NCCL all-gather")
-    ap.add_argument("--step-mode", type=int, default=1, choices=[0, 1], help="1 GPU: 1 = persistent loop kernel, 0 = CUDA graph")
+    ap.add_argument("--step-mode", type=int, default=0, choices=[0, 1], help="1 GPU: 0 = CUDA graph (default), 1 = persistent loop kernel")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     return ap.parse_args()
 

@@ -76,4 +76,4 @@ for n in [int(a) for a in (sys.argv[1:] or ["100000"])]:
             print("  loop kernel, CTA 0 cycles per block step:", {k: round(v / nst) for k, v in pr.items()})
         k1, u1, _ = g.energies()
         print("  dE/E", ((k0 + u0) - (k1 + u1)) / (k1 + u1), "t=", tnow)
-    ctx.set_step_mode(1)
+    ctx.set_step_mode(0)

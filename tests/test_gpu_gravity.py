@@ -29,7 +29,7 @@ def grav(pkg, ctx, request):
     g = pkg.GravityCore(ctx=ctx)  # the session shares one context: reset its clock and parameters
     g.set_time(0.0)
     yield g
-    ctx.set_step_mode(1)
+    ctx.set_step_mode(0)
 
 
 @pytest.mark.parametrize("n", [2, 3, 33, 257, 1000, 4096])
@@ -231,7 +231,6 @@ def test_full_size_properties_1e6(pkg, ctx):
     n = 1_000_000
     c = pkg.ic.cluster(n, seed=7, require_massive=False)
     p = [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
-    ctx.set_step_mode(1)
     g = pkg.GravityCore(ctx=ctx)
     g.set_time(0.0)
     g.commit(*p)
