@@ -53,9 +53,9 @@ struct StagingView {
   double *t, *dt;
   unsigned int *tag;  // id of the block step that wrote the record
 };
-struct MboxEntry {
-  unsigned long long tmin_bits;  // sender's min(t+dt) candidate for the next block time
-  unsigned long long tag;        // id of the block step the sender has completed
+struct MboxEntry {  // two self-validating words: (step id low 32 bits) << 32 | one half of the sender's candidate time
+  unsigned long long tmin_bits;  // ... | high half of min(t+dt)
+  unsigned long long tag;        // ... | low half
 };
 __host__ __device__ inline size_t staging_parity_bytes(int n) {
   return ((size_t)n * (4 * 32 + 2 * 8 + 4) + 255) & ~(size_t)255;

@@ -128,29 +128,45 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// returns false on error; tmin_out = global minimum of the ranks' candidates (the next block time)
+// returns false on error; tmin_out = global minimum of the ranks' candidates (the next block time).
+// Mailbox entry of (parity, source rank): two self-validating 64-bit words, each carrying the low 32 bits of the
+// step id next to one half of the candidate time, so the two stores need no fence between them and a reader can
+// never pair a new tag with an old value.  did_store: this CTA issued peer stores in the corrector phase (only
+// those CTAs pay a system-scope fence before arriving; the others fence at gpu scope).
 __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target, const unsigned n_ctas,
-                                             const unsigned long long step_id, const StepCtrl *nxt,
+                                             const unsigned long long step_id, const StepCtrl *nxt, const bool did_store,
                                              unsigned long long *sh_tmin, unsigned long long &tmin_out) {
   GravHeader *hdr = g.hdr;
   const int par = (int)(step_id & 1ull);
+  const unsigned long long tag = (step_id & 0xffffffffull) << 32;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (did_store) __threadfence_system();
+    else __threadfence();
     target += n_ctas;
     const unsigned old = atomicAdd(&hdr->bar_counter, 1u);
     if (old == target - 1u) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
       __threadfence_system();
       const unsigned long long lm = ld_volatile_u64(&nxt->t_next_bits);
-      for (int q = 0; q < g.world; q++) st_volatile_u64(&(mbox_of(g.slab[q], g.n_tot) + par * MAX_PEERS + g.rank)->tmin_bits, lm);
-      __threadfence_system();
-      for (int q = 0; q < g.world; q++) st_volatile_u64(&(mbox_of(g.slab[q], g.n_tot) + par * MAX_PEERS + g.rank)->tag, step_id);
+      const unsigned long long w0 = tag | (lm >> 32), w1 = tag | (lm & 0xffffffffull);
+      for (int q = 0; q < g.world; q++) {
+        MboxEntry *mb = mbox_of(g.slab[q], g.n_tot) + par * MAX_PEERS + g.rank;
+        st_volatile_u64(&mb->tmin_bits, w0);
+        st_volatile_u64(&mb->tag, w1);
+      }
     }
     const MboxEntry *mine = mbox_of(g.slab[g.rank], g.n_tot) + par * MAX_PEERS;
     unsigned spins = 0;
     bool ok = true;
+    unsigned long long tm = INF_BITS;
     for (int q = 0; q < g.world && ok; q++) {
-      while (ld_volatile_u64(&mine[q].tag) != step_id) {
+      while (true) {
+        const unsigned long long w0 = ld_volatile_u64(&mine[q].tmin_bits), w1 = ld_volatile_u64(&mine[q].tag);
+        if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) {
+          const unsigned long long v = (w0 << 32) | (w1 & 0xffffffffull);
+          tm = v < tm ? v : tm;
+          break;
+        }
         if (++spins > LOOP_SPIN_LIMIT) {
           atomicExch(&hdr->loop_error, 2);
           ok = false;
@@ -164,11 +180,6 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
     }
     __threadfence_system();
     asm volatile("fence.proxy.async;" ::: "memory");
-    unsigned long long tm = INF_BITS;
-    for (int q = 0; q < g.world; q++) {
-      const unsigned long long v = ld_volatile_u64(&mine[q].tmin_bits);
-      tm = v < tm ? v : tm;
-    }
     *sh_tmin = tm;
   }
   __syncthreads();
@@ -223,7 +234,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     if (n_act > 0) force_items<C>(g, sm, cur, n_act, n_ctas, it);
     if (!grid_barrier(g.hdr, target, n_ctas)) break;
     if (n_act > 0) phase_correct<MODE, true>(g, nxt, n_act, tn, blockIdx.x, n_ctas, sh, shr, this_id);
-    if (!dist_barrier(g, target, n_ctas, this_id, nxt, &sh_tmin, tnext_bits)) break;
+    const bool did_store = n_act > 0 && (int)blockIdx.x < n_act;  // superset of the CTAs that corrected a slot
+    if (!dist_barrier(g, target, n_ctas, this_id, nxt, did_store, &sh_tmin, tnext_bits)) break;
     step_id = this_id;
     ph = (ph + 1) % 3;
     if (first) g.ctrl[ph].t_next_bits = tnext_bits;  // the global next block time, for the host / the next launch

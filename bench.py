@@ -118,6 +118,7 @@ class ClockSampler:
 def cpu_sample(pkg, c, span, pair_budget):
     """The CPU oracle on the same ICs: initial full force + block steps until the pair budget."""
     from oracle import hermite as H
+    H.use_all_cores()
     n = len(c["m"])
     o = H.HermiteOracle(n)
     o.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
@@ -141,6 +142,7 @@ def run_reference(args):
     pkg = importlib.import_module("26al-nbody_b200")
     c, cv, span = workload(pkg, args.n, args.seed, args.dt_myr)
     from oracle import hermite as H
+    H.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it may run on
     n = args.n
     o = H.HermiteOracle(n)
     o.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])

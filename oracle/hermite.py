@@ -56,6 +56,8 @@ def lib():
         L.orc_energies.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
         L.orc_force.argtypes = ([C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32, C.c_int] + [_D] * 7)
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_counters.restype = None
         L.orc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
@@ -170,4 +172,14 @@ class HermiteOracle:
 
 
 def num_threads():
+    return lib().orc_num_threads()
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for its children)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(int(n))
     return lib().orc_num_threads()

@@ -501,6 +501,15 @@ int orc_energies(orc_t *o, double *kinetic, double *potential, double *sum_mm_ov
   return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm of bench.py asks for all host cores */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
