@@ -28,13 +28,15 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
   return v;
 }
 
-// returns false when the launch must be abandoned (error flag raised by some CTA)
+// returns false when the launch must be abandoned (error flag raised by some CTA).
+// Arrival is a release-RED at gpu scope (orders the CTA's earlier writes, made visible to thread 0 by the
+// bar.sync), the spin is a relaxed volatile load, and one acquire fence after the spin (ptxas: CCTL.IVALL +
+// MEMBAR) makes the other CTAs' writes visible to every thread released by the trailing bar.sync.
 __device__ __forceinline__ bool grid_barrier(GravHeader *hdr, unsigned &target, const unsigned n_ctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     target += n_ctas;
-    atomicAdd(&hdr->bar_counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&hdr->bar_counter) : "memory");
     unsigned spins = 0;
     while (ld_volatile_u32(&hdr->bar_counter) < target) {
       if (++spins > LOOP_SPIN_LIMIT) {
@@ -43,7 +45,7 @@ __device__ __forceinline__ bool grid_barrier(GravHeader *hdr, unsigned &target, 
       }
       if ((spins & 0xfff) == 0 && ld_volatile_u32((const unsigned *)&hdr->loop_error)) break;
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");  // later TMA reads must see the generic-proxy writes
   }
   __syncthreads();

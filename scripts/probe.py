@@ -6,6 +6,20 @@ pkg = importlib.import_module("26al-nbody_b200")
 ctx = pkg.Context(0)
 print("device", ctx.device_info())
 print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+if os.environ.get("PROBE_LATENCY"):
+    for n in (1000, 10000, 100000):
+        c = pkg.ic.cluster(n, seed=0)
+        for mode in (1, 0):
+            ctx.set_step_mode(mode)
+            g = pkg.GravityCore(ctx=ctx)
+            g.set_time(0.0)
+            g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+            g.evolve(2.0 ** -9)
+            steps, pairs = g.evolve(2.0 ** -9 + 2.0 ** -5)
+            ms, _ = g.last_device_ms()
+            print(f"N={n} mode={'loop' if mode else 'graph'}: {steps} steps, {ms*1e3/steps:.2f} us/step, {pairs/ms*1e-6:.1f} Gpairs/s", flush=True)
+    ctx.set_step_mode(0)
+    sys.exit(0)
 if os.environ.get("PROBE_BIGBLOCK"):
     n = 100000
     c = pkg.ic.cluster(n, seed=0)
