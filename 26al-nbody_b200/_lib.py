@@ -67,6 +67,7 @@ SIGNATURES = {
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
     "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),
     "al26_set_big_block": (C.c_int, [_VP, C.c_int]),
+    "al26_set_decomposition": (C.c_int, [_VP, C.c_int, C.c_double]),
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
@@ -177,6 +178,9 @@ class Context:
 
     def set_big_block(self, n_act_min):
         self.chk(self.L.al26_set_big_block(self.h, int(n_act_min)))
+
+    def set_decomposition(self, max_rounds=32, item_overhead_pairs=3200.0):
+        self.chk(self.L.al26_set_decomposition(self.h, int(max_rounds), float(item_overhead_pairs)))
 
     def set_step_mode(self, mode):
         self.chk(self.L.al26_set_step_mode(self.h, int(mode)))

@@ -107,7 +107,8 @@ struct GravDev {
 constexpr int FORCE_TJ = 256;      // j per TMA tile (2 x 8 KB per stage)
 constexpr int FORCE_STAGES = 3;
 constexpr int FORCE_MIN_JCHUNK = 64;
-constexpr int FORCE_MAX_ROUNDS = 16;             // work items per CTA at most (load balance for big blocks)
+constexpr int FORCE_MAX_ROUNDS = 32;             // default: work items per CTA at most (load balance for big blocks)
+constexpr int FORCE_MAX_ROUNDS_CAP = 64;         // upper limit of the tunable (sizes the partial buffers)
 constexpr double FORCE_ITEM_OVERHEAD_PAIRS = 3200.0;  // fixed cost of one item (TMA prologue, barriers, reduction) in pair units
 constexpr int FORCE_BIG_NACT_DEFAULT = 2048;      // n_act >= GravDev::big_nact: the configuration's IPT i-particles per lane
 constexpr int FORCE_SPLIT_MAX_NACT = 16;         // n_act <= this: lanes split over j as well (tiny blocks)
@@ -127,12 +128,13 @@ struct Decomp {
 // last round is full) to maximise  (fill of the last round) x (item work / (item work + fixed item cost)):
 // small blocks get one round of big items, big blocks get many rounds so the tail stays short.
 // The search runs on the HOST once per commit (decomp_table); kernels only look the answer up.
-inline int choose_jsplit(int n_itiles, int ti, int n_tot, int grid) {
+inline int choose_jsplit(int n_itiles, int ti, int n_tot, int grid, int max_rounds = FORCE_MAX_ROUNDS,
+                         double overhead_pairs = FORCE_ITEM_OVERHEAD_PAIRS) {
   int max_by_j = n_tot / FORCE_MIN_JCHUNK;
   if (max_by_j < 1) max_by_j = 1;
   int best_ns = 1, prev = 0;
   double best_eff = -1.0;
-  for (int k = 1; k <= FORCE_MAX_ROUNDS; k++) {
+  for (int k = 1; k <= max_rounds; k++) {
     int ns = (int)(((long long)k * grid) / n_itiles);
     if (ns > max_by_j) ns = max_by_j;
     if (ns < 1) ns = 1;
@@ -141,7 +143,7 @@ inline int choose_jsplit(int n_itiles, int ti, int n_tot, int grid) {
     const long long items = (long long)n_itiles * ns;
     const long long rounds = (items + grid - 1) / grid;
     const double w = (double)ti * (double)((n_tot + ns - 1) / ns);
-    const double eff = ((double)items / (double)(rounds * grid)) * (w / (w + FORCE_ITEM_OVERHEAD_PAIRS));
+    const double eff = ((double)items / (double)(rounds * grid)) * (w / (w + overhead_pairs));
     if (eff > best_eff) {
       best_eff = eff;
       best_ns = ns;
@@ -155,11 +157,12 @@ inline int decomp_small_entries(int big_nact) { return (big_nact + 31) / 32 + 1;
 inline int decomp_table_entries(int n_loc, int ipt_big, int big_nact) {
   return decomp_small_entries(big_nact) + (n_loc + 32 * ipt_big - 1) / (32 * ipt_big) + 2;
 }
-inline void fill_decomp_table(int *tab, int n_loc, int n_tot, int grid, int ipt_big, int big_nact) {
+inline void fill_decomp_table(int *tab, int n_loc, int n_tot, int grid, int ipt_big, int big_nact,
+                              int max_rounds = FORCE_MAX_ROUNDS, double overhead_pairs = FORCE_ITEM_OVERHEAD_PAIRS) {
   const int ns_small = decomp_small_entries(big_nact);
-  for (int t = 1; t <= ns_small; t++) tab[t - 1] = choose_jsplit(t, 32, n_tot, grid);
+  for (int t = 1; t <= ns_small; t++) tab[t - 1] = choose_jsplit(t, 32, n_tot, grid, max_rounds, overhead_pairs);
   const int nb = decomp_table_entries(n_loc, ipt_big, big_nact) - ns_small;
-  for (int t = 1; t <= nb; t++) tab[ns_small + t - 1] = choose_jsplit(t, 32 * ipt_big, n_tot, grid);
+  for (int t = 1; t <= nb; t++) tab[ns_small + t - 1] = choose_jsplit(t, 32 * ipt_big, n_tot, grid, max_rounds, overhead_pairs);
 }
 
 __host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, const int *__restrict__ tab, int ipt_big, int big_nact) {
@@ -182,7 +185,7 @@ __host__ __device__ inline Decomp make_decomp(int n_act, int n_tot, const int *_
 
 // partial-buffer entries that cover every n_act in [0, n_loc]
 inline long long part_capacity(int n_loc, int grid) {
-  return (long long)n_loc + 32 * FORCE_IPT_MAX + (long long)(FORCE_MAX_ROUNDS * grid + 1) * 32 * FORCE_IPT_MAX * 2;
+  return (long long)n_loc + 32 * FORCE_IPT_MAX + (long long)(FORCE_MAX_ROUNDS_CAP * grid + 1) * 32 * FORCE_IPT_MAX * 2;
 }
 
 // ---- launchers (each enqueues on `s`; returns the number of kernels launched) ----

@@ -93,6 +93,8 @@ struct al26_ctx {
   int dbg_phase = 0;
   int force_variant = 0;
   int big_nact = FORCE_BIG_NACT_DEFAULT;  // tuning: block size from which the force kernel holds several i per lane
+  int max_rounds = FORCE_MAX_ROUNDS;      // tuning: work items per CTA at most
+  double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
   int step_mode = 0;      // 1 GPU: 0 = CUDA graph of 3 kernels per block step (default, measured ~2-9 % faster), 1 = persistent cooperative loop kernel
   bool coop_ok = false;   // device supports cooperative launch
   cudaGraphExec_t graph = nullptr;
@@ -677,7 +679,7 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   {
     g.big_nact = c->big_nact;
     std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt, g.big_nact));
-    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact);
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact, c->max_rounds, c->item_overhead);
     int *d_tab = nullptr;
     CU(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
     CU(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1040,7 +1042,7 @@ int al26_grav_force(al26_ctx *c, int64_t n, double eps2, const double *m, const 
   {
     g.big_nact = c->big_nact;
     std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt, g.big_nact));
-    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact);
+    fill_decomp_table(tab.data(), g.n_loc, g.n_tot, g.grid_force, g.force_ipt, g.big_nact, c->max_rounds, c->item_overhead);
     TRY(cudaMalloc(&d_tab, tab.size() * sizeof(int)));
     TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     g.decomp_tab = d_tab;
@@ -1133,6 +1135,16 @@ int al26_set_big_block(al26_ctx *c, int n_act_min) {
   if (n_act_min < 33 || n_act_min > (1 << 20)) return fail(c, AL26_EINVAL, "big-block threshold %d out of range", n_act_min);
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_big_block during evolve");
   c->big_nact = n_act_min;  // takes effect at the next commit
+  return 0;
+}
+
+int al26_set_decomposition(al26_ctx *c, int max_rounds, double item_overhead_pairs) {
+  if (!c) return AL26_EINVAL;
+  if (max_rounds < 1 || max_rounds > FORCE_MAX_ROUNDS_CAP || !(item_overhead_pairs >= 0.0))
+    return fail(c, AL26_EINVAL, "decomposition: max_rounds in [1, %d], overhead >= 0", FORCE_MAX_ROUNDS_CAP);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_decomposition during evolve");
+  c->max_rounds = max_rounds;  // takes effect at the next commit
+  c->item_overhead = item_overhead_pairs;
   return 0;
 }
 

@@ -115,6 +115,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic_bytes(kernel_csv):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full summary under profiles/ (one capture per change; None if the file is not there)."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", kernel_csv)):
+            f = line.strip().split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
+                tot += float(f[2]) * scale
+        return tot or None
+    except Exception:
+        return None
+
+
 def cpu_sample(pkg, c, span, pair_budget):
     """The CPU oracle on the same ICs: initial full force + block steps until the pair budget."""
     from oracle import hermite as H
@@ -305,7 +320,9 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "DFMA-only microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "frac_of_nominal_37.2": achieved_tf / nominal_tf, "flop_per_pair": FLOP_PER_PAIR,
-                "pairs_per_launch": f_pairs, "ms_per_launch": f_ms, "traffic": None}
+                "pairs_per_launch": f_pairs, "ms_per_launch": f_ms,
+                "algorithmic_bytes_per_launch": 64.0 * n, "traffic": ncu_traffic_bytes("r01_k_force_ncu_full.csv") if n == 100_000 and world == 1 else None,
+                "traffic_source": "profiles/r01_k_force_ncu_full.csv (ncu --set full, same kernel and launch shape)"}
 
     # ---- device-resident arm: K evolve calls, CUDA events on the library stream ----------------
     k0, u0, _ = g.energies()

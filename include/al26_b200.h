@@ -137,6 +137,10 @@ int al26_set_force_variant(al26_ctx *ctx, int variant);
 /* tuning hook: active blocks of at least n_act_min particles use the configuration's several i-particles
  * per lane (default 2048); applies at the next al26_grav_commit */
 int al26_set_big_block(al26_ctx *ctx, int n_act_min);
+/* tuning hook: parameters of the force kernel's work decomposition (al26_internal.cuh: choose_jsplit): at most
+ * max_rounds work items per CTA (default 32) and the fixed cost of one item in pair units (default 3200);
+ * applies at the next al26_grav_commit */
+int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_pairs);
 /* tuning hook: how block steps are driven on one GPU.  0 (default): a CUDA graph of three kernels per block
  * step, relaunched until the device reports the call done; 1: one persistent cooperative kernel runs the
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).

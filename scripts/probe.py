@@ -6,6 +6,23 @@ pkg = importlib.import_module("26al-nbody_b200")
 ctx = pkg.Context(0)
 print("device", ctx.device_info())
 print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+if os.environ.get("PROBE_DECOMP"):
+    n = 100000
+    c = pkg.ic.cluster(n, seed=0)
+    for mr, ov in ((16, 3200.0), (8, 3200.0), (32, 3200.0), (64, 3200.0), (32, 1000.0), (16, 8000.0), (32, 8000.0)):
+        ctx.set_decomposition(mr, ov)
+        g = pkg.GravityCore(ctx=ctx)
+        g.set_time(0.0)
+        g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+        row = []
+        for na, reps in ((0, 3), (20000, 5), (5000, 10), (1000, 20), (300, 20), (100, 20)):
+            ms, pairs = g.bench_force(reps, n_act=na)
+            row.append(f"{na or n}:{pairs/ms*1e-6:.0f}G")
+        steps, pairs = g.evolve(2.0 ** -5)
+        ms, _ = g.last_device_ms()
+        print(f"max_rounds {mr} overhead {ov}: " + " ".join(row) + f" | evolve 2^-5: {ms:.1f} ms {pairs/ms*1e-6:.1f} G", flush=True)
+    ctx.set_decomposition()
+    sys.exit(0)
 if os.environ.get("PROBE_LATENCY"):
     for n in (1000, 10000, 100000):
         c = pkg.ic.cluster(n, seed=0)
