@@ -278,10 +278,8 @@ void slice_of(int64_t n, int rank, int world, int64_t &i0, int64_t &nloc) {
   nloc = i1 - i0;
 }
 
-// all-gather the predicted / snapshot j-set; no-op on one GPU.  Slices are equal-sized
-// only when world divides n, so the gather is done as `world` broadcasts-by-allgather of the max
-// slice into a padded layout would waste bandwidth; instead require equal slices (n % world == 0
-// is enforced at commit) and use one in-place ncclAllGather per array.
+// NCCL mode: all-gather the predicted / snapshot j-set, one in-place ncclAllGather per array;
+// slices are equal (n % world == 0 is enforced at commit).  No-op on one GPU and in peer-memory mode.
 int gather_j(al26_ctx *c) {
   if (c->world == 1 || is_p2p(c)) return 0;  // peer-memory mode: the state is replicated, nothing to gather
   const GravDev &g = c->g;
