@@ -60,6 +60,7 @@ SIGNATURES = {
     "al26_grav_dbg_begin": (C.c_int, [_VP, C.c_double]),
     "al26_grav_dbg_advance": (C.c_int, [_VP, C.c_int64, _PI64, _PINT]),
     "al26_grav_dbg_finish": (C.c_int, [_VP]),
+    "al26_grav_dbg_profile_steps": (C.c_int, [_VP, C.c_int, _PD]),
     "al26_grav_force": (C.c_int, [_VP, C.c_int64, C.c_double] + [_D] * 7 + [C.c_int64, _I32] + [_D] * 7),
     "al26_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
     "al26_enrich_last_kernel_ms": (C.c_int, [_VP, _PD]),

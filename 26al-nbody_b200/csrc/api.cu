@@ -844,6 +844,40 @@ int al26_grav_dbg_advance(al26_ctx *c, int64_t max_steps, int64_t *n_done, int *
   return 0;
 }
 
+int al26_grav_dbg_profile_steps(al26_ctx *c, int reps, double *us3) {
+  if (!c || !us3) return AL26_EINVAL;
+  if (!c->in_evolve) return fail(c, AL26_ESTATE, "dbg_profile_steps outside begin/finish");
+  if (c->world != 1) return fail(c, AL26_ESTATE, "dbg_profile_steps is a single-GPU diagnostic");
+  CU(cudaSetDevice(c->device));
+  cudaEvent_t ev[4];
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  double acc[3] = {0, 0, 0};
+  int done_steps = 0;
+  for (int r = 0; r < reps; r++) {
+    CU(cudaEventRecord(ev[0], c->stream));
+    c->launches += launch_predict_list(c->g, MODE_STEP, c->dbg_phase, c->stream);
+    CU(cudaEventRecord(ev[1], c->stream));
+    c->launches += launch_force(c->g, c->dbg_phase, c->stream);
+    CU(cudaEventRecord(ev[2], c->stream));
+    c->launches += launch_correct(c->g, MODE_STEP, c->dbg_phase, c->stream);
+    CU(cudaEventRecord(ev[3], c->stream));
+    CU(cudaEventSynchronize(ev[3]));
+    c->dbg_phase = (c->dbg_phase + 1) % 3;
+    int rc = read_header(c);
+    if (rc) return rc;
+    if (c->h_hdr->done) break;
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      acc[k] += ms * 1e3;
+    }
+    done_steps++;
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  for (int k = 0; k < 3; k++) us3[k] = done_steps ? acc[k] / done_steps : 0.0;
+  return 0;
+}
+
 int al26_grav_dbg_finish(al26_ctx *c) {
   if (!c) return AL26_EINVAL;
   if (!c->in_evolve) return fail(c, AL26_ESTATE, "dbg_finish outside begin");

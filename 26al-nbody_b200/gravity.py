@@ -113,6 +113,12 @@ class GravityCore:
     def finish(self):
         self.ctx.chk(self.L.al26_grav_dbg_finish(self.h))
 
+    def profile_steps(self, reps=200):
+        """(between begin and finish) mean microseconds of the predict, force and correct kernels per block step"""
+        us = (C.c_double * 3)()
+        self.ctx.chk(self.L.al26_grav_dbg_profile_steps(self.h, int(reps), us))
+        return dict(zip(("predict", "force", "correct"), list(us)))
+
     def force(self, m, x, y, z, vx, vy, vz, idx=None, eps2=0.0):
         """One K1 evaluation on caller arrays: acc(3), jerk(3), pot on the listed particles."""
         arrs = [_lib.f64(a) for a in (m, x, y, z, vx, vy, vz)]

@@ -114,6 +114,9 @@ int al26_grav_get_last_active(al26_ctx *ctx, int64_t cap, int32_t *idx, int64_t 
 int al26_grav_dbg_begin(al26_ctx *ctx, double t_end);
 int al26_grav_dbg_advance(al26_ctx *ctx, int64_t max_steps, int64_t *n_done, int *finished);
 int al26_grav_dbg_finish(al26_ctx *ctx);
+/* diagnostic (between dbg_begin and dbg_finish, one GPU): run up to `reps` block steps as individual launches
+ * with CUDA events around each kernel; us3 = mean microseconds of predict+schedule, force, correct */
+int al26_grav_dbg_profile_steps(al26_ctx *ctx, int reps, double *us3);
 /* one force evaluation (K1) on caller arrays: acc, jerk, pot on the n_act listed particles */
 int al26_grav_force(al26_ctx *ctx, int64_t n, double eps2, const double *m, const double *x, const double *y,
                     const double *z, const double *vx, const double *vy, const double *vz, int64_t n_act,

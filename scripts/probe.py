@@ -6,6 +6,19 @@ pkg = importlib.import_module("26al-nbody_b200")
 ctx = pkg.Context(0)
 print("device", ctx.device_info())
 print("fp64 peak TF/s (dfma microkernel):", ctx.fp64_peak_tflops())
+if os.environ.get("PROBE_KERNELS"):
+    for n in (1000, 10000, 100000):
+        c = pkg.ic.cluster(n, seed=0)
+        ctx.set_step_mode(0)
+        g = pkg.GravityCore(ctx=ctx)
+        g.set_time(0.0)
+        g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
+        g.evolve(2.0 ** -9)
+        g.begin(2.0 ** -9 + 2.0 ** -5)
+        pr = g.profile_steps(400)
+        g.advance(-1); g.finish()
+        print(f"N={n}: per-kernel us (individual launches, events in between): " + ", ".join(f"{k} {v:.2f}" for k, v in pr.items()), flush=True)
+    sys.exit(0)
 if os.environ.get("PROBE_DECOMP"):
     n = 100000
     c = pkg.ic.cluster(n, seed=0)

@@ -245,3 +245,20 @@ def test_full_size_properties_1e6(pkg, ctx):
     assert vec_rel([c_[idx] for c_ in a[:3]], ref[:3]) < TOL and vec_rel([c_[idx] for c_ in a[3:6]], ref[3:6]) < TOL
     t, dt = g.get_timesteps()
     assert np.all(np.log2(dt) == np.round(np.log2(dt))) and dt.max() <= 2.0 ** -5
+
+
+def test_figure_eight_known_answer_on_gpu(pkg, grav):
+    """the author's informal three-body check (notes.md:19) as a known answer: period 6.32591398, E = -1.287146"""
+    from test_oracle_hermite import figure_eight
+    m, *ps = figure_eight()
+    grav.set_params(eta=0.02)
+    grav.commit(m, *ps)
+    k0, u0, _ = grav.energies()
+    assert k0 + u0 == pytest.approx(-1.287146, rel=1e-5)
+    grav.evolve(6.32591398)
+    st = grav.get_state()
+    for a, b in zip(st[1:], ps):
+        assert np.max(np.abs(a - b)) < 5e-5
+    k1, u1, _ = grav.energies()
+    assert abs((k1 + u1) - (k0 + u0)) / abs(k0 + u0) < 1e-8
+    grav.set_params()

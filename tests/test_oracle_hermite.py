@@ -141,3 +141,34 @@ def test_set_mass_reinitialises_and_time_setter():
     assert np.allclose(o.get_acc_jerk()[0], 2.0 * a0, rtol=1e-12)
     o.evolve(5.01)
     assert o.get_time() == 5.01
+
+
+def figure_eight():
+    """Chenciner & Montgomery (2000) figure-eight choreography, G = m = 1 (the author's informal
+    three-body check, notes.md:19); initial conditions from Simo's table, period 6.32591398."""
+    r1 = np.array([0.97000436, -0.24308753, 0.0])
+    v3 = np.array([-0.93240737, -0.86473146, 0.0])
+    pos = np.stack([r1, -r1, np.zeros(3)])
+    vel = np.stack([-0.5 * v3, -0.5 * v3, v3])
+    return np.ones(3), pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), vel[:, 0].copy(), vel[:, 1].copy(), vel[:, 2].copy()
+
+
+def test_figure_eight_three_body_returns_after_one_period():
+    m, *ps = figure_eight()
+    o = H.HermiteOracle(3, eta=0.02)
+    o.commit(m, *ps)
+    k0, u0, _ = o.energies()
+    assert k0 + u0 == pytest.approx(-1.287146, rel=1e-5)  # the choreography's energy
+    T = 6.32591398
+    o.evolve(T / 3.0)                                      # after T/3 the bodies have cycled places: 1 -> 2 -> 3 -> 1 (up to labelling)
+    st = o.get_state()
+    third = np.stack(st[1:4]).T
+    start = np.stack(ps[:3]).T
+    d = [min(np.linalg.norm(third[i] - start[j]) for j in range(3)) for i in range(3)]
+    assert max(d) < 2e-5
+    o.evolve(T)
+    st = o.get_state()
+    for a, b in zip(st[1:], ps):
+        assert np.max(np.abs(a - b)) < 5e-5                # back at the start after one period
+    k1, u1, _ = o.energies()
+    assert abs((k1 + u1) - (k0 + u0)) / abs(k0 + u0) < 1e-8
