@@ -73,6 +73,7 @@ SIGNATURES = {
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
+    "al26_local_densities": (C.c_int, [_VP, C.c_int64, _D, _D, _D, _D, _D]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     "al26_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
@@ -200,6 +201,13 @@ class Context:
         tf = C.c_double(0)
         self.chk(self.L.al26_bench_fp64_peak(self.h, C.byref(tf)))
         return tf.value
+
+    def local_densities(self, x_pc, y_pc, z_pc, mass_msun):
+        """`local_densities_numba` of the reference's plotting script (plotting/al26_plot.py:324-359) on the GPU."""
+        a = [f64(v) for v in (x_pc, y_pc, z_pc, mass_msun)]
+        rho = np.zeros(len(a[0]))
+        self.chk(self.L.al26_local_densities(self.h, len(rho), *a, rho))
+        return rho
 
     def last_device_ms(self):
         ms, nl = C.c_double(0), C.c_int64(0)

@@ -262,4 +262,8 @@ struct InterloperParams {
 };
 int launch_interloper(const EnrichDev &e, const InterloperParams &p, cudaStream_t s);
 
+// post-processing (analysis.cu)
+int launch_local_density(int n, const double *x, const double *y, const double *z, const double *m, double *rho,
+                         cudaStream_t s);
+
 }  // namespace al26

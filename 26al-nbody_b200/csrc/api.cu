@@ -1231,6 +1231,29 @@ int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {
   return 0;
 }
 
+int al26_local_densities(al26_ctx *c, int64_t n, const double *x_pc, const double *y_pc, const double *z_pc,
+                         const double *mass_msun, double *rho) {
+  if (!c) return AL26_EINVAL;
+  if (n < 11 || n > 0x7fffffff / 2) return fail(c, AL26_EINVAL, "local_densities needs at least 11 stars (10 neighbours), got %lld", (long long)n);
+  if (!x_pc || !y_pc || !z_pc || !mass_msun || !rho) return fail(c, AL26_EINVAL, "null array");
+  CU(cudaSetDevice(c->device));
+  const size_t nt = (size_t)n;
+  double *d = nullptr;
+  CU(cudaMalloc(&d, 5 * nt * sizeof(double)));
+  cudaError_t e = cudaSuccess;
+  const double *src[4] = {x_pc, y_pc, z_pc, mass_msun};
+  for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaMemcpyAsync(d + k * nt, src[k], nt * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    c->launches += launch_local_density((int)n, d, d + nt, d + 2 * nt, d + 3 * nt, d + 4 * nt, c->stream);
+    e = cudaMemcpyAsync(rho, d + 4 * nt, nt * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(c, AL26_ECUDA, "al26_local_densities: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- enrichment ---------------------------------------------------------------------------
 
 int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const double *tau_disk_myr,

@@ -20,6 +20,7 @@ UNITS = [
     ("hermite_step.cu", ["--fmad=false"]),
     ("hermite_loop.cu", ["--fmad=false"]),
     ("enrich.cu", ["--fmad=false"]),
+    ("analysis.cu", ["--fmad=false"]),
     ("api.cu", ["--fmad=false"]),
 ]
 DEPS = ["al26_internal.cuh", "hermite_force.cuh", "hermite_step.cuh", os.path.join("..", "..", "include", "al26_b200.h")]

@@ -158,6 +158,14 @@ int al26_grav_loop_profile(al26_ctx *ctx, int64_t *cycles6);
  * the roofline denominator of the force kernel */
 int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);
 
+/* ---- post-processing ------------------------------------------------------------------
+ * replaces: `local_densities_numba(x, y, z, masses)` (plotting/al26_plot.py:324-359, called by
+ * calc_local_densities :361-371): 10-nearest-neighbour local density of every star, rho = sum of the ten nearest
+ * masses / (4.18879020479 d10^3), positions in pc, masses in Msun -> Msun/pc^3.  O(N) memory instead of the
+ * reference's N x N matrix; bit-identical results.  n >= 11. */
+int al26_local_densities(al26_ctx *ctx, int64_t n, const double *x_pc, const double *y_pc, const double *z_pc,
+                         const double *mass_msun, double *rho);
+
 /* ---- enrichment (state lives on the device between calls) ---------------------------*/
 /* replaces: the per-star cluster attributes set in init_cluster (al26_nbody.py:1543-1603):
  * r_disk [km], tau_disk [Myr], disk_alive, kicked, wind_ratio_26al/60fe, sn_yield_26al/60fe [kg].

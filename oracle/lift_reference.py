@@ -43,6 +43,20 @@ def lift(names=WANTED, path=REFERENCE_FILE):
     return {n: ns[n] for n in names if n in ns}
 
 
+PLOT_FILE = "/root/reference/plotting/al26_plot.py"
+
+
+def lift_plotting(names=("local_densities_numba",), path=PLOT_FILE):
+    """Lift numba functions of the reference's post-processing script (plotting/al26_plot.py:324-359)."""
+    from numba import njit, prange
+    with open(path) as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    picked = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    ns = {"np": np, "njit": njit, "prange": prange}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), ns)
+    return {n: ns[n] for n in names if n in ns}
+
+
 def make_wind_case(rng, n, n_hm, frac_lm=0.5, length_km=3.0e13, bubble_km=3.0856775814913e12):
     """A seeded synthetic input set for calc_wind_abs in the reference's units."""
     x, y, z = (rng.normal(0.0, length_km, n) for _ in range(3))
@@ -105,6 +119,14 @@ def generate(out_path):
                                             b_old[0, i], b_old[1, i], b_old[2, i], b_new[0, i], b_new[1, i], b_new[2, i], 0.1)
                    for i in range(m)])
     out["isect_a_old"], out["isect_a_new"], out["isect_b_old"], out["isect_b_new"], out["isect_frac"] = a_old, a_new, b_old, b_new, fr
+    # local densities (plotting/al26_plot.py:324-359): 10-nearest-neighbour density of every star
+    ld = lift_plotting()["local_densities_numba"]
+    rng = np.random.default_rng(21)
+    for tag, nn in (("ld_a", 64), ("ld_b", 1500)):
+        px, py, pz = (rng.normal(0, 1.0, nn) * (1.0 + 3.0 * (rng.random(nn) < 0.2)) for _ in range(3))
+        pm = 10.0 ** rng.uniform(-2, 2, nn)
+        out[tag + "_x"], out[tag + "_y"], out[tag + "_z"], out[tag + "_m"] = px, py, pz, pm
+        out[tag + "_rho"] = ld(px, py, pz, pm)
     np.savez_compressed(out_path, **out)
     return out
 

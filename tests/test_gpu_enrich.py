@@ -184,3 +184,27 @@ def test_interloper_vs_reference_golden_and_oracle(pkg, ctx, golden):
     hit[5] = False
     assert np.array_equal(inv[R["agb26"]][:m] > 0, hit) and inv[R["agb26"]][-1] == 0.0 and raw[0, 5] == 0.0
     assert np.all(raw[0][:m][hit] > inv[R["agb26"]][:m][hit])  # the inventory decays, raw does not
+
+
+@pytest.mark.parametrize("tag", ["ld_a", "ld_b"])
+def test_local_densities_bit_exact_vs_reference_golden(pkg, ctx, golden, tag):
+    """plotting/al26_plot.py:324-359: bit-exact against the reference's own numba function"""
+    rho = ctx.local_densities(golden[tag + "_x"], golden[tag + "_y"], golden[tag + "_z"], golden[tag + "_m"])
+    assert np.array_equal(rho, golden[tag + "_rho"])
+
+
+def test_local_densities_large_sample_vs_oracle(pkg, ctx):
+    from oracle import analysis_oracle as ao
+    c = pkg.ic.cluster(20000, seed=3)
+    rho = ctx.local_densities(c["x"], c["y"], c["z"], c["m_msun"])
+    idx = np.random.default_rng(0).choice(20000, 40, replace=False)
+    x, y, z, m = c["x"], c["y"], c["z"], c["m_msun"]
+    for i in idx:  # the oracle is O(N) per star
+        d = np.sqrt((x[i] - x) * (x[i] - x) + (y[i] - y) * (y[i] - y) + (z[i] - z) * (z[i] - z))
+        nr = np.argsort(d, kind="stable")[1:11]
+        mass = 0.0
+        for j in nr:
+            mass += m[j]
+        assert rho[i] == mass / (ao.FTP * d[nr[-1]] * d[nr[-1]] * d[nr[-1]])
+    with pytest.raises(pkg.Al26Error):
+        ctx.local_densities(x[:5], y[:5], z[:5], m[:5])

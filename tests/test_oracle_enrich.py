@@ -122,3 +122,10 @@ def test_intersection_bit_exact_vs_reference_golden(golden):
     mine = np.array([eo.calc_intersection(*a0, *a1, *b0[:, i], *b1[:, i], 0.1) for i in range(b0.shape[1])])
     assert np.array_equal(mine, fr) and np.count_nonzero(fr) > 20
     assert eo.calc_intersection(-1, 0, 0, 1, 0, 0, 0, 0.05, 0, 0, 0.05, 0, 0.1) == 0.0859375
+
+
+@pytest.mark.parametrize("tag", ["ld_a", "ld_b"])
+def test_local_density_oracle_bit_exact_vs_reference_golden(golden, tag):
+    from oracle import analysis_oracle as ao
+    rho = ao.local_densities(golden[tag + "_x"], golden[tag + "_y"], golden[tag + "_z"], golden[tag + "_m"])
+    assert np.array_equal(rho, golden[tag + "_rho"])
