@@ -66,6 +66,7 @@ SIGNATURES = {
     "al26_enrich_last_kernel_ms": (C.c_int, [_VP, _PD]),
     "al26_grav_bench_force": (C.c_int, [_VP, C.c_int, _PD, _PI64]),
     "al26_grav_bench_force_n": (C.c_int, [_VP, C.c_int64, C.c_int, _PD, _PI64]),
+    "al26_dbg_decomposition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PI64]),
     "al26_set_force_variant": (C.c_int, [_VP, C.c_int]),
     "al26_set_big_block": (C.c_int, [_VP, C.c_int]),
     "al26_set_decomposition": (C.c_int, [_VP, C.c_int, C.c_double]),
@@ -213,6 +214,15 @@ class Context:
         ms, nl = C.c_double(0), C.c_int64(0)
         self.chk(self.L.al26_last_device_ms(self.h, C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
+
+
+def decomposition(n_act, n_tot, sm_count=148, variant=0, big_nact=2048):
+    """host-only: the force kernel's work decomposition (dict) for a block of n_act among n_tot particles"""
+    out = (C.c_int64 * 8)()
+    rc = load().al26_dbg_decomposition(int(n_act), int(n_tot), int(sm_count), int(variant), int(big_nact), out)
+    if rc != 0:
+        raise Al26Error(rc, "bad arguments")
+    return dict(zip(("ipt", "ti", "n_itiles", "n_jsplit", "jchunk", "slot_stride", "part_capacity", "grid"), list(out)))
 
 
 def dist_unique_id():

@@ -1154,6 +1154,20 @@ int al26_grav_bench_force(al26_ctx *c, int reps, double *avg_ms, int64_t *pairs_
   return al26_grav_bench_force_n(c, 0, reps, avg_ms, pairs_per_eval);
 }
 
+int al26_dbg_decomposition(int n_act, int n_tot, int sm_count, int variant, int big_nact, int64_t *out8) {
+  // host-only (no device, no context): the work decomposition the kernels would use, for CPU-side invariant tests
+  int minb = 2, ipt = 2;
+  if (!out8 || n_act < 1 || n_tot < 1 || n_act > n_tot || sm_count < 1 || big_nact < 33) return AL26_EINVAL;
+  if (force_variant_info(variant, &minb, &ipt)) return AL26_EINVAL;
+  const int grid = minb * sm_count;
+  std::vector<int> tab(decomp_table_entries(n_tot, ipt, big_nact));
+  fill_decomp_table(tab.data(), n_tot, n_tot, grid, ipt, big_nact);
+  const Decomp d = make_decomp(n_act, n_tot, tab.data(), ipt, big_nact);
+  out8[0] = d.ipt; out8[1] = d.ti; out8[2] = d.n_itiles; out8[3] = d.n_jsplit; out8[4] = d.jchunk;
+  out8[5] = d.slot_stride; out8[6] = part_capacity(n_tot, grid); out8[7] = grid;
+  return 0;
+}
+
 int al26_set_force_variant(al26_ctx *c, int variant) {
   if (!c) return AL26_EINVAL;
   if (variant < 0 || variant >= force_variant_count()) return fail(c, AL26_EINVAL, "force variant %d out of range", variant);

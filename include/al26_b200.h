@@ -134,6 +134,10 @@ int al26_grav_bench_force(al26_ctx *ctx, int reps, double *avg_ms, int64_t *pair
 /* same with only the first n_act (<= 0: all) local particles active: the small-block regime */
 int al26_grav_bench_force_n(al26_ctx *ctx, int64_t n_act, int reps, double *avg_ms, int64_t *pairs_per_eval);
 
+/* host-only diagnostic (needs no GPU): the force kernel's work decomposition for a block of n_act active
+ * particles among n_tot: out8 = {i per lane, i per item, i-tiles, j-chunks, j per chunk, slot stride,
+ * partial-buffer capacity, CTAs} */
+int al26_dbg_decomposition(int n_act, int n_tot, int sm_count, int variant, int big_nact, int64_t *out8);
 /* tuning hook: pick one of the compiled force-kernel configurations (0 = default); applies at the
  * next al26_grav_commit */
 int al26_set_force_variant(al26_ctx *ctx, int variant);

@@ -130,3 +130,33 @@ def test_decay_fractions_literal(pkg):
     assert (f26, f60) == eo.decay_fractions(0.01)  # same call as the reference (np.exp)
     # SURVEY 8(c) golden; np.exp may differ by 1 ulp between SIMD dispatch paths
     assert f26 == pytest.approx(0.99037925616650468, rel=3e-16) and f60 == pytest.approx(0.99733760048885856, rel=3e-16)
+
+
+def test_force_work_decomposition_invariants(pkg):
+    """host-side check of the table the force and corrector kernels share (al26_internal.cuh: choose_jsplit,
+    make_decomp): every block size maps to a decomposition that covers all i and all j, fits the partial
+    buffers, fills the grid when there is enough work, and never cuts items finer than a TMA-friendly chunk."""
+    lib = importlib.import_module("26al-nbody_b200._lib")
+    rng = np.random.default_rng(0)
+    for variant in range(4):
+        for n_tot in (1, 31, 1000, 10_000, 100_000, 1_000_000):
+            acts = sorted({1, 2, 16, 17, 32, 33, 2047, 2048, 2049, n_tot, max(1, n_tot // 2), max(1, n_tot // 3)}
+                          | set(int(v) for v in rng.integers(1, n_tot + 1, 12)))
+            for n_act in acts:
+                if n_act > n_tot:
+                    continue
+                d = lib.decomposition(n_act, n_tot, variant=variant)
+                assert d["ti"] == 32 * d["ipt"] and d["ipt"] >= 1
+                assert d["n_itiles"] * d["ti"] >= n_act > (d["n_itiles"] - 1) * d["ti"]      # all i, no empty tile
+                assert d["n_jsplit"] * d["jchunk"] >= n_tot > (d["n_jsplit"] - 1) * d["jchunk"]  # all j, no empty chunk
+                assert d["jchunk"] % 8 == 0
+                assert d["slot_stride"] == d["n_itiles"] * d["ti"]
+                assert d["n_jsplit"] * d["slot_stride"] <= d["part_capacity"]
+                items = d["n_itiles"] * d["n_jsplit"]
+                if n_act * n_tot >= 64 * 64 * d["grid"]:
+                    assert items >= 0.5 * d["grid"], (variant, n_tot, n_act, d)              # the grid is used
+                assert items <= 64 * d["grid"] + d["n_itiles"]
+                if d["ipt"] > 1:
+                    assert n_act >= 2048
+    with pytest.raises(lib.Al26Error):
+        lib.decomposition(5, 3)
