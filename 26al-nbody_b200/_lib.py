@@ -41,6 +41,7 @@ SIGNATURES = {
     "al26_dist_unique_id": (C.c_int, [_VP]),
     "al26_dist_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "al26_dist_set_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_dist_set_split_min": (C.c_int, [_VP, C.c_int]),
     "al26_dist_p2p_export": (C.c_int, [_VP, _VP]),
     "al26_dist_p2p_import": (C.c_int, [_VP, _VP, C.c_int]),
     "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -153,11 +154,12 @@ class Context:
         self.chk(self.L.al26_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(fr), C.byref(tot)))
         return {"sm_count": sm.value, "clock_khz": khz.value, "free_bytes": fr.value, "total_bytes": tot.value}
 
-    def dist_init(self, rank, world, unique_id_bytes, mode="p2p", exchange=None):
+    def dist_init(self, rank, world, unique_id_bytes, mode="p2p", exchange=None, split_min=0):
         """mode "p2p": peer-memory exchange (default), "nccl": all-gather path.  `exchange(bytes) -> list of
         bytes` all-gathers a 64-byte blob across ranks (dist.py provides one over torch.distributed); it is
         called after every gravity commit in p2p mode."""
         self.chk(self.L.al26_dist_set_mode(self.h, 1 if mode == "p2p" else 0))
+        self.chk(self.L.al26_dist_set_split_min(self.h, int(split_min)))
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
         self.chk(self.L.al26_dist_init(self.h, int(rank), int(world), C.cast(buf, C.c_void_p) if buf else None))
         self.rank, self.world = int(rank), int(world)

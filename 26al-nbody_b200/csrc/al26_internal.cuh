@@ -37,6 +37,8 @@ struct GravHeader {
   int pad2;
   unsigned long long dist_step;  // id of the last block step completed in peer-memory mode
   unsigned long long dist_tnext_bits;  // the global next block time after it
+  int dist_prev_exch;                  // the last block step was an exchanged one (its staged records are still to be pulled)
+  int pad3;
   long long loop_cycles[6];  // diagnostic: CTA 0's SM cycles in predict / barrier / force / barrier / correct / barrier
 };
 
@@ -99,6 +101,8 @@ struct GravDev {
   double4 *raw_a, *raw_j;
   // peer-memory mode
   int rank, world, p2p;
+  int *list_own;   // active particles this rank owns (i % world == rank); `list` holds ALL active ones
+  int split_min;   // block steps with fewer active particles are computed redundantly by every rank (no exchange)
   void *slab[MAX_PEERS];  // slab[q]: rank q's staging slab as mapped in this process (slab[rank] = own)
 };
 

@@ -83,6 +83,7 @@ struct al26_ctx {
   void *slab = nullptr;          // own staging slab (peer-memory mode)
   bool p2p_ready = false;        // peers' slabs imported
   unsigned long long dist_step = 0;
+  int split_min = 0;             // peer-memory mode: exchange only block steps with at least this many active particles (0 = auto)
 
   // gravity
   GravDev g{};
@@ -191,6 +192,7 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
     ctrl[i].t_next_bits = INF_BITS;
     ctrl[i].n_act = 0;
     ctrl[i].work_counter = 0;
+    ctrl[i].pad[0] = 0;
   }
   if (i == 0 && zero_counters) {
     hdr->n_steps = 0;
@@ -253,7 +255,7 @@ void free_gravity(al26_ctx *c) {
   c->slab = nullptr;
   c->p2p_ready = false;
   void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr,
-                  (void *)g.decomp_tab};
+                  (void *)g.decomp_tab, g.list_own};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   g = GravDev{};
@@ -584,6 +586,14 @@ int al26_dist_set_mode(al26_ctx *c, int mode) {
   return 0;
 }
 
+int al26_dist_set_split_min(al26_ctx *c, int n_act_min) {
+  if (!c) return AL26_EINVAL;
+  if (n_act_min < 0) return fail(c, AL26_EINVAL, "split threshold must be >= 0 (0 = automatic)");
+  if (c->committed) return fail(c, AL26_ESTATE, "al26_dist_set_split_min must precede commit");
+  c->split_min = n_act_min;
+  return 0;
+}
+
 int al26_dist_p2p_export(al26_ctx *c, void *out64) {
   if (!c || !out64) return AL26_EINVAL;
   if (!is_p2p(c) || !c->committed || !c->slab) return fail(c, AL26_ESTATE, "p2p_export needs a committed peer-memory context");
@@ -650,6 +660,13 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
     CU(cudaMemset(c->slab, 0, slab_bytes((int)n)));
     g.slab[c->rank] = c->slab;
     c->dist_step = 0;
+    CU(cudaMalloc(&g.list_own, (size_t)nloc * sizeof(int)));
+    // splitting a block step over the ranks pays once the force work saved exceeds the ~20 us an exchange costs:
+    // (1 - 1/P) n_act N / (4.7e11 pairs/s) > 20 us
+    long long auto_min = (long long)(20e-6 * 4.7e11 / (double)n * (double)c->world / (double)(c->world - 1)) + 1;
+    if (auto_min < 8) auto_min = 8;
+    if (auto_min > 8192) auto_min = 8192;
+    g.split_min = c->split_min > 0 ? c->split_min : (int)auto_min;
   }
   {
     int minb = 2, ipt = 2;

@@ -191,7 +191,7 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
 
 template <class C, int MODE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
-    k_loop_dist(const GravDev g, const int phase0, const int max_steps, const unsigned long long step_id0) {
+    k_loop_dist(const GravDev g, const int phase0, const int max_steps, const unsigned long long xid0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
   __shared__ unsigned long long sh[C::THREADS / 32];
@@ -204,10 +204,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   unsigned target = 0;
   int ph = phase0;
   const double span = g.hdr->span;
-  unsigned long long step_id = step_id0;   // id of the last completed step; this launch starts with step_id0 + 1
-  // the next block time: written by k_begin (identical on every rank: the state is replicated) or by the
-  // previous launch
+  // Exchanges are numbered (xid); a block step with few active particles is NOT exchanged: the state is
+  // replicated, so every rank computes all of its active particles itself -- bit-identical on every rank (same
+  // code, same inputs, fixed reduction order) -- with no NVLink traffic and no cross-GPU barrier.  The decision is
+  // a function of the global active count, hence the same on every rank; ranks drift apart during such steps
+  // and meet again at the next exchange.
+  unsigned long long xid = xid0;
+  bool prev_exch = (MODE == MODE_STEP) && g.hdr->dist_prev_exch != 0;
+  // the next block time: written by k_begin (identical on every rank) or by the previous launch
   unsigned long long tnext_bits = __ldcg(&g.ctrl[phase0].t_next_bits);
+  GravDev gown = g;
+  gown.list = g.list_own;
   for (int step = 0; step < max_steps; step++) {
     StepCtrl *cur = &g.ctrl[ph];
     StepCtrl *nxt = &g.ctrl[(ph + 1) % 3];
@@ -224,28 +231,44 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     } else {
       tn = span;
     }
-    const unsigned long long this_id = step_id + 1;
-    phase_predict_list<MODE, true>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh, step_id);
+    phase_predict_list<MODE, true>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh, prev_exch ? xid : 0ull);
     if (first) {
       old->t_next_bits = INF_BITS;
       old->n_act = 0;
       old->work_counter = 0;
+      old->pad[0] = 0;
     }
     if (!grid_barrier(g.hdr, target, n_ctas)) break;
-    const int n_act = __ldcg(&cur->n_act);
-    if (n_act > 0) force_items<C>(g, sm, cur, n_act, n_ctas, it);
-    if (!grid_barrier(g.hdr, target, n_ctas)) break;
-    if (n_act > 0) phase_correct<MODE, true>(g, nxt, n_act, tn, blockIdx.x, n_ctas, sh, shr, this_id);
-    const bool did_store = n_act > 0 && (int)blockIdx.x < n_act;  // superset of the CTAs that corrected a slot
-    if (!dist_barrier(g, target, n_ctas, this_id, nxt, did_store, &sh_tmin, tnext_bits)) break;
-    step_id = this_id;
+    const int n_all = __ldcg(&cur->n_act);
+    const int n_own = __ldcg(&cur->pad[0]);
+    const bool exchange = (MODE != MODE_STEP) || n_all >= g.split_min;
+    if (!exchange) {
+      // ---- redundant step: all active particles, local stores, local barrier ----
+      if (n_all > 0) force_items<C>(g, sm, cur, n_all, n_ctas, it);
+      if (!grid_barrier(g.hdr, target, n_ctas)) break;
+      if (n_all > 0) phase_correct<MODE_STEP, false>(g, nxt, n_all, tn, blockIdx.x, n_ctas, sh, shr, 0ull, n_own);
+      if (!grid_barrier(g.hdr, target, n_ctas)) break;
+      tnext_bits = __ldcg(&nxt->t_next_bits);
+      prev_exch = false;
+    } else {
+      // ---- exchanged step: own share, peer stores, cross-GPU barrier ----
+      const unsigned long long this_id = xid + 1;
+      if (n_own > 0) force_items<C>(gown, sm, cur, n_own, n_ctas, it);
+      if (!grid_barrier(g.hdr, target, n_ctas)) break;
+      if (n_own > 0) phase_correct<MODE, true>(gown, nxt, n_own, tn, blockIdx.x, n_ctas, sh, shr, this_id);
+      const bool did_store = n_own > 0 && (int)blockIdx.x < n_own;  // superset of the CTAs that corrected a slot
+      if (!dist_barrier(g, target, n_ctas, this_id, nxt, did_store, &sh_tmin, tnext_bits)) break;
+      xid = this_id;
+      prev_exch = true;
+    }
     ph = (ph + 1) % 3;
-    if (first) g.ctrl[ph].t_next_bits = tnext_bits;  // the global next block time, for the host / the next launch
+    if (first) g.ctrl[ph].t_next_bits = tnext_bits;  // the next block time, for the host / the next launch
   }
   if (first) {
     g.hdr->phase = ph;
-    g.hdr->dist_step = step_id;
+    g.hdr->dist_step = xid;
     g.hdr->dist_tnext_bits = tnext_bits;
+    g.hdr->dist_prev_exch = (MODE == MODE_STEP && prev_exch) ? 1 : 0;  // init / sync steps are pulled by k_pull
   }
 }
 

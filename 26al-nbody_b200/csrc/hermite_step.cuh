@@ -57,8 +57,10 @@ __device__ __forceinline__ void block_min_to(unsigned long long v, unsigned long
 // Predict every local particle to `tn` into the global j-set, build the active list of this step in
 // cur->n_act / g.list, and fold min(t+dt) of the non-active particles into nxt->t_next_bits.
 // (block_id, n_blocks) describe the caller's grid; every block runs the same number of iterations.
-// DIST (peer-memory mode): the state is replicated; first pull the records peers staged during block step
-// `pull_tag` (parity pull_tag & 1) into the local state, and list only the active particles this rank owns.
+// DIST (peer-memory mode): the state is replicated; first pull the records peers staged during exchange
+// `pull_tag` (parity pull_tag & 1; 0 = nothing to pull) into the local state; build BOTH the list of all active
+// particles (g.list, cur->n_act) and the list of those this rank owns (g.list_own, cur->pad[0]) -- the loop
+// kernel decides after the barrier which one this step uses.
 template <int MODE, bool DIST>
 __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
                                                    const int block_id, const int n_blocks, unsigned long long *sh,
@@ -103,7 +105,6 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
         const unsigned long long cb = dbits(c);
         c_min = cb < c_min ? cb : c_min;
       }
-      if (DIST && (i % g.world) != g.rank) active = false;  // somebody else's particle
     }
     // ballot compaction (order within the list is irrelevant to the results: every slot's force sum
     // runs over j in a fixed order)
@@ -114,6 +115,17 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
       if (lane == (__ffs(m) - 1)) b0 = atomicAdd(&cur->n_act, __popc(m));
       b0 = __shfl_sync(0xffffffffu, b0, __ffs(m) - 1);
       if (active) g.list[b0 + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+    if (DIST) {
+      const bool mine = active && (i % g.world) == g.rank;
+      const unsigned mo = __ballot_sync(0xffffffffu, mine);
+      if (mo) {
+        const int lane = threadIdx.x & 31;
+        int b0 = 0;
+        if (lane == (__ffs(mo) - 1)) b0 = atomicAdd(&cur->pad[0], __popc(mo));
+        b0 = __shfl_sync(0xffffffffu, b0, __ffs(mo) - 1);
+        if (mine) g.list_own[b0 + __popc(mo & ((1u << lane) - 1u))] = i;
+      }
     }
   }
   if (MODE == MODE_STEP) block_min_to(c_min, &nxt->t_next_bits, sh);
@@ -240,7 +252,8 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, co
 template <int MODE, bool DIST>
 __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, const int n_act, const double tn,
                                               const int block_id, const int n_blocks, unsigned long long *sh,
-                                              double (*shr)[7], const unsigned long long step_id = 0) {
+                                              double (*shr)[7], const unsigned long long step_id = 0,
+                                              const int count_n = -1) {
   const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt, g.big_nact);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -295,7 +308,8 @@ __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, c
   if (MODE == MODE_STEP) block_min_to(c_bits, &nxt->t_next_bits, sh);
   if (block_id == 0 && threadIdx.x == 0 && MODE != MODE_RAW) {
     if (MODE != MODE_INIT) g.hdr->n_steps += 1;
-    g.hdr->n_pairs += (long long)n_act * (long long)g.n_tot;
+    // count_n: the particles whose pairs this rank accounts for (its own share when a step is computed redundantly)
+    g.hdr->n_pairs += (long long)(count_n >= 0 ? count_n : n_act) * (long long)g.n_tot;
     int b = 0;
     while ((1 << (b + 1)) <= n_act && b < 31) b++;
     g.hdr->nact_hist[b] += 1;  // diagnostic: log2 histogram of the block sizes

@@ -45,13 +45,13 @@ def allgather_bytes(blob, world, device="cpu", group=None):
     return [p.cpu().numpy().tobytes() for p in parts]
 
 
-def init_context(ctx, rank, world, device="cuda", group=None, mode="p2p"):
+def init_context(ctx, rank, world, device="cuda", group=None, mode="p2p", split_min=0):
     """Join `ctx` (an al26 Context on this rank's GPU) to the job: NCCL communicator (energies, and the
     all-gather path when mode == "nccl") plus, in the default peer-memory mode, the hook that swaps the
     staging slabs' IPC handles after every commit."""
     if world == 1:
         return ctx
     uid = broadcast_unique_id(_lib.dist_unique_id, rank, device=device, group=group)
-    ctx.dist_init(rank, world, uid, mode=mode,
+    ctx.dist_init(rank, world, uid, mode=mode, split_min=split_min,
                   exchange=lambda blob: allgather_bytes(blob, world, device=device, group=group))
     return ctx

@@ -67,6 +67,10 @@ int al26_dist_init(al26_ctx *ctx, int rank, int world, const void *nccl_unique_i
  * block step, no NCCL in the loop.  0: contiguous i-slices, NCCL all-gather of the predicted j-set + an
  * 8-byte min-reduce per block step. */
 int al26_dist_set_mode(al26_ctx *ctx, int mode);
+/* peer-memory mode (before commit): block steps with fewer than n_act_min active particles are not exchanged --
+ * the state is replicated, so every rank computes them itself, bit-identically, with no NVLink traffic and no
+ * cross-GPU barrier; 0 = automatic (the block size at which the force work saved outweighs an exchange, ~2e7/N) */
+int al26_dist_set_split_min(al26_ctx *ctx, int n_act_min);
 /* peer-memory mode, after every al26_grav_commit: export this rank's slab as a 64-byte CUDA IPC handle, let
  * the host all-gather the handles (torch.distributed), import the world x 64 bytes */
 int al26_dist_p2p_export(al26_ctx *ctx, void *out64);

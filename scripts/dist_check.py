@@ -15,7 +15,7 @@ from oracle import enrich_oracle as eo
 
 ctx = pkg.Context(local)
 MODE = os.environ.get("AL26_DIST_MODE", "p2p")
-pkg.dist.init_context(ctx, rank, world, device="cuda", mode=MODE)
+pkg.dist.init_context(ctx, rank, world, device="cuda", mode=MODE, split_min=int(os.environ.get("AL26_SPLIT_MIN", "0")))
 
 n = 4096
 c = pkg.ic.cluster(n, seed=7)
