@@ -72,6 +72,9 @@ SIGNATURES = {
     "al26_set_big_block": (C.c_int, [_VP, C.c_int]),
     "al26_set_decomposition": (C.c_int, [_VP, C.c_int, C.c_double]),
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_set_fuse_max": (C.c_int, [_VP, C.c_int]),
+    "al26_grav_fused_steps": (C.c_int, [_VP, _PI64]),
+    "al26_grav_fuse_profile": (C.c_int, [_VP, _PI64]),
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
@@ -189,6 +192,21 @@ class Context:
 
     def set_step_mode(self, mode):
         self.chk(self.L.al26_set_step_mode(self.h, int(mode)))
+
+    def set_fuse_max(self, n_act_max):
+        """loop kernels: largest block that takes the fused small-step path (0 = off); before commit"""
+        self.chk(self.L.al26_set_fuse_max(self.h, int(n_act_max)))
+
+    def fused_steps(self):
+        n = C.c_int64(0)
+        self.chk(self.L.al26_grav_fused_steps(self.h, C.byref(n)))
+        return n.value
+
+    def fuse_profile(self):
+        h = (C.c_int64 * 16)()
+        self.chk(self.L.al26_grav_fuse_profile(self.h, h))
+        names = ("force_arrive", "wait_partials", "reduce_correct", "-", "wait_release", "fused_total", "scan", "barrier")
+        return {k: v for k, v in zip(names, list(h)) if k != "-"}
 
     def block_histogram(self):
         h = (C.c_int64 * 32)()

@@ -19,8 +19,8 @@ constexpr unsigned long long INF_BITS = 0x7FF0000000000000ull;  // +inf as order
 struct StepCtrl {
   unsigned long long t_next_bits;  // min over particles of (t + dt), as ordered bits of a double >= 0
   int n_act;                       // entries in the active list
-  int work_counter;                // dynamic work-item counter of the force kernel
-  int pad[4];
+  int work_counter;                // dynamic work-item counter of the force kernel; fused steps: CTAs whose partials are stored
+  int pad[4];                      // [0] peer-memory mode: active particles this rank owns; [1] fused steps: slots corrected
 };
 
 struct GravHeader {
@@ -40,9 +40,24 @@ struct GravHeader {
   int dist_prev_exch;                  // the last block step was an exchanged one (its staged records are still to be pulled)
   int pad3;
   long long loop_cycles[6];  // diagnostic: CTA 0's SM cycles in predict / barrier / force / barrier / correct / barrier
+  long long n_fused;             // diagnostic: block steps taken through the fused path, since the last commit
+  long long fuse_ns[16];         // diagnostic (builds with -DAL26_FUSE_TIMING only): globaltimer ns per fused-step segment
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
+
+// ---- fused small block steps of the persistent loop kernels (hermite_loop.cu): the scheduler pass leaves every
+// active particle's predicted state and old force in this compact record, so the force phase and the correcting
+// CTA fetch everything they need in one round trip.  One buffer is enough: a step's readers all finish before
+// the step's release word is published.
+constexpr int FUSE_CAP = 32;  // largest block handled by the fused path
+constexpr int FUSE_AUTO_MAX_N = 32768;  // automatic setting: fused path on for N <= this many particles
+struct ActBuf {
+  double4 pos[FUSE_CAP], vel[FUSE_CAP];  // predicted {x,y,z,m}, {vx,vy,vz,-}
+  double4 acc[FUSE_CAP], jrk[FUSE_CAP];  // force at the start of the step
+  double2 tdt[FUSE_CAP];                 // {t, dt}
+  int idx[FUSE_CAP];
+};
 
 // ---- peer-memory multi-GPU mode: every rank holds the full state; a rank corrects the
 // active particles it owns (i % world == rank) and stores their new state straight into EVERY rank's staging
@@ -89,6 +104,7 @@ struct GravDev {
   const int *decomp_tab;  // n_jsplit by number of i-tiles (fill_decomp_table)
   int big_nact;           // blocks of at least this many particles use force_ipt i-particles per lane
   double eps2, eta, dt_max, dt_min;
+  double Dmax;  // largest step of the current call's dyadic ladder (= hdr->D; set by the host at begin_evolve)
   double4 *pos, *vel, *acc, *jrk;
   double *t, *dt;
   double4 *jpos, *jvel;
@@ -101,6 +117,10 @@ struct GravDev {
   double4 *raw_a, *raw_j;
   // peer-memory mode
   int rank, world, p2p;
+  // fused small block steps (loop kernels; needs n_loc == n_tot and a j-chunk per CTA that fits the stage buffers)
+  ActBuf *act;
+  int fuse_max;   // block steps of at most this many active particles take the fused path (0 = off)
+  int fuse_jc;    // particles per CTA: CTA b owns [b * fuse_jc, (b + 1) * fuse_jc)
   int *list_own;   // active particles this rank owns (i % world == rank); `list` holds ALL active ones
   int split_min;   // block steps with fewer active particles are computed redundantly by every rank (no exchange)
   void *slab[MAX_PEERS];  // slab[q]: rank q's staging slab as mapped in this process (slab[rank] = own)

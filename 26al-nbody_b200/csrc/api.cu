@@ -95,6 +95,7 @@ struct al26_ctx {
   int force_variant = 0;
   int big_nact = FORCE_BIG_NACT_DEFAULT;  // tuning: block size from which the force kernel holds several i per lane
   int max_rounds = FORCE_MAX_ROUNDS;      // tuning: work items per CTA at most
+  int fuse_max = -1;                      // loop kernels: block steps of at most this many particles take the fused path (0 = off, -1 = by N)
   double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
   int step_mode = 0;      // 1 GPU: 0 = CUDA graph of 3 kernels per block step (default, measured ~2-9 % faster), 1 = persistent cooperative loop kernel
   bool coop_ok = false;   // device supports cooperative launch
@@ -193,6 +194,7 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
     ctrl[i].n_act = 0;
     ctrl[i].work_counter = 0;
     ctrl[i].pad[0] = 0;
+    ctrl[i].pad[1] = 0;
   }
   if (i == 0 && zero_counters) {
     hdr->n_steps = 0;
@@ -255,7 +257,7 @@ void free_gravity(al26_ctx *c) {
   c->slab = nullptr;
   c->p2p_ready = false;
   void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr,
-                  (void *)g.decomp_tab, g.list_own};
+                  (void *)g.decomp_tab, g.list_own, g.act};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   g = GravDev{};
@@ -426,6 +428,7 @@ int begin_evolve(al26_ctx *c, double t_end) {
   if (c->dirty && (rc = initialise_forces(c))) return rc;
   double D = pow2floor_h(span);
   if (D > c->dt_max) D = c->dt_max;
+  c->g.Dmax = D;
   reset_ctrl(c, 0);
   c->launches += launch_begin(c->g, span, D, c->stream);
   if ((rc = reduce_tnext(c, 0))) return rc;
@@ -691,6 +694,18 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   CU(cudaMalloc(&g.part_j, (size_t)g.part_cap * sizeof(double4)));
   CU(cudaMalloc(&g.ctrl, 3 * sizeof(StepCtrl)));
   CU(cudaMalloc(&g.hdr, sizeof(GravHeader)));
+  CU(cudaMalloc(&g.act, sizeof(ActBuf)));
+  CU(cudaMemsetAsync(g.act, 0, sizeof(ActBuf), c->stream));
+  {  // fused small steps: one contiguous chunk of particles per CTA, held in the force kernel's stage buffers
+    int jc = (int)((nloc + g.grid_force - 1) / g.grid_force);
+    jc = (jc + 7) & ~7;
+    g.fuse_jc = jc;
+    const bool ok = (g.n_loc == g.n_tot) && jc <= FORCE_STAGES * FORCE_TJ;
+    // automatic: on where block steps are latency-bound (measured on B200, one and two GPUs: from N ~ 5e4 up the ~4 us
+    // saved per small step are cancelled by the fused kernel's ~1 % slower big-block force loop)
+    const int want = c->fuse_max >= 0 ? c->fuse_max : (n <= FUSE_AUTO_MAX_N ? FUSE_CAP : 0);
+    g.fuse_max = ok ? want : 0;
+  }
   {
     g.big_nact = c->big_nact;
     std::vector<int> tab(decomp_table_entries(g.n_loc, g.force_ipt, g.big_nact));
@@ -1208,6 +1223,34 @@ int al26_set_decomposition(al26_ctx *c, int max_rounds, double item_overhead_pai
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_decomposition during evolve");
   c->max_rounds = max_rounds;  // takes effect at the next commit
   c->item_overhead = item_overhead_pairs;
+  return 0;
+}
+
+int al26_set_fuse_max(al26_ctx *c, int n_act_max) {
+  if (!c) return AL26_EINVAL;
+  if (n_act_max < -1 || n_act_max > FUSE_CAP) return fail(c, AL26_EINVAL, "fuse_max in [-1, %d]", FUSE_CAP);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_fuse_max during evolve");
+  c->fuse_max = n_act_max;  // takes effect at the next commit
+  return 0;
+}
+
+int al26_grav_fused_steps(al26_ctx *c, int64_t *n_fused) {
+  if (!c || !n_fused) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "fused_steps before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  *n_fused = c->h_hdr->n_fused;
+  return 0;
+}
+
+int al26_grav_fuse_profile(al26_ctx *c, int64_t *ns8) {  // 16 values
+  if (!c || !ns8) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "fuse_profile before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  for (int k = 0; k < 16; k++) ns8[k] = c->h_hdr->fuse_ns[k];
   return 0;
 }
 

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libal26b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"] + ARCH
+COMMON += os.environ.get("AL26_NVCC_EXTRA", "").split()  # e.g. -DAL26_FUSE_TIMING (diagnostic builds)
 # --fmad=false everywhere: the corrector / ladder / enrichment arithmetic has to follow the oracle's and the
 # reference's evaluation order bit for bit; the force kernel writes every FMA explicitly (fma()), so the
 # flag does not change its SASS.

@@ -131,6 +131,89 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
   if (MODE == MODE_STEP) block_min_to(c_min, &nxt->t_next_bits, sh);
 }
 
+// The scheduler pass of the persistent loop kernels when the fused small-step path is on (MODE_STEP only, state
+// not sliced: n_loc == n_tot).  Same work as phase_predict_list, but every CTA owns a CONTIGUOUS chunk
+// [j0, j0 + cnt) whose predicted particles it also keeps in its own shared memory (sp / sv, cnt <= the stage
+// buffers' capacity), and every active particle's predicted state + old force go to the compact record g.act, so
+// a small block step needs neither the TMA pipeline nor dependent loads through the list.
+template <bool DIST>
+__device__ __forceinline__ void phase_scan_chunk(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
+                                                 const int j0, const int cnt, double4 *sp, double4 *sv,
+                                                 unsigned long long *sh, const unsigned long long pull_tag = 0) {
+  unsigned long long c_min = INF_BITS;
+  StagingView sview;
+  if (DIST) sview = staging_view(g.slab[g.rank], g.n_tot, (int)(pull_tag & 1ull));
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < cnt; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    const int i = j0 + k;
+    bool active = false;
+    double4 pp, pv, a, j;
+    double ti = 0.0, dti = 0.0;
+    if (k < cnt) {
+      double4 p, v;
+      if (DIST && pull_tag != 0ull && sview.tag[i] == (unsigned int)pull_tag) {  // staged by its owner in the previous exchange
+        p = sview.pos[i]; v = sview.vel[i]; a = sview.acc[i]; j = sview.jrk[i];
+        ti = sview.t[i]; dti = sview.dt[i];
+        g.pos[i] = p; g.vel[i] = v; g.acc[i] = a; g.jrk[i] = j;
+        g.t[i] = ti; g.dt[i] = dti;
+      } else {
+        p = g.pos[i]; v = g.vel[i]; a = g.acc[i]; j = g.jrk[i];
+        ti = g.t[i]; dti = g.dt[i];
+      }
+      const double s = tn - ti;
+      const double s2 = s * s * 0.5, s3 = s * s * s * (1.0 / 6.0);
+      pp.x = p.x + v.x * s + a.x * s2 + j.x * s3;
+      pp.y = p.y + v.y * s + a.y * s2 + j.y * s3;
+      pp.z = p.z + v.z * s + a.z * s2 + j.z * s3;
+      pp.w = p.w;
+      pv.x = v.x + a.x * s + j.x * s2;
+      pv.y = v.y + a.y * s + j.y * s2;
+      pv.z = v.z + a.z * s + j.z * s2;
+      pv.w = 0.0;
+      sp[k] = pp;
+      sv[k] = pv;
+      g.jpos[i] = pp;  // the big-block path (TMA) and the parity hooks read the global copy
+      g.jvel[i] = pv;
+      const double c = ti + dti;
+      active = (c == tn);
+      if (!active) {
+        const unsigned long long cb = dbits(c);
+        c_min = cb < c_min ? cb : c_min;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (m) {
+      int b0 = 0;
+      if (lane == (__ffs(m) - 1)) b0 = atomicAdd(&cur->n_act, __popc(m));
+      b0 = __shfl_sync(0xffffffffu, b0, __ffs(m) - 1);
+      if (active) {
+        const int slot = b0 + __popc(m & ((1u << lane) - 1u));
+        g.list[slot] = i;
+        if (slot < FUSE_CAP) {
+          ActBuf *ab = g.act;
+          ab->pos[slot] = pp; ab->vel[slot] = pv; ab->acc[slot] = a; ab->jrk[slot] = j;
+          ab->tdt[slot] = make_double2(ti, dti);
+          ab->idx[slot] = i;
+        }
+      }
+    }
+    if (DIST) {
+      const bool mine = active && (i % g.world) == g.rank;
+      const unsigned mo = __ballot_sync(0xffffffffu, mine);
+      if (mo) {
+        int b0 = 0;
+        if (lane == (__ffs(mo) - 1)) b0 = atomicAdd(&cur->pad[0], __popc(mo));
+        b0 = __shfl_sync(0xffffffffu, b0, __ffs(mo) - 1);
+        if (mine) g.list_own[b0 + __popc(mo & ((1u << lane) - 1u))] = i;
+      }
+    }
+  }
+  // the stage buffers were written through the generic proxy; a later TMA refill is an async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  block_min_to(c_min, &nxt->t_next_bits, sh);
+}
+
 // Aarseth estimate; mirrors oracle/hermite_oracle.c: aarseth()
 __device__ __forceinline__ double aarseth(const double eta, const double a1[3], const double j1[3],
                                           const double a2[3], const double a3[3]) {
@@ -165,45 +248,29 @@ __device__ __forceinline__ void store_state(const GravDev &g, const int i, const
   }
 }
 
-// corrector + ladder for one active slot, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}; tn = the
-// block time (MODE_STEP) or the span (MODE_SYNC)
+// what the corrector needs to know about one active particle besides its new force
+struct SlotIn {
+  int i;
+  double4 a0, j0;  // force at the start of the step
+  double4 xp, vp;  // predicted position (w = mass) and velocity
+  double t, dt;
+};
+
+// corrector + ladder for one active particle, given its reduced force r[7] = {ax,ay,az,jx,jy,jz,pot}; tn = the
+// block time (MODE_STEP) or the span (MODE_SYNC); Dmax = the largest step of the call's ladder (hdr->D)
 template <int MODE, bool DIST>
-__device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, const int slot, const double r[7],
-                                           unsigned long long &c_bits, const unsigned long long step_id) {
-  if (MODE == MODE_RAW) {
-    g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
-    g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
-    return;
-  }
-  const int i = g.list[slot];
+__device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, const SlotIn &in, const double r[7],
+                                             unsigned long long &c_bits, const unsigned long long step_id,
+                                             const double Dmax) {
+  const int i = in.i;
   const double a1[3] = {r[0], r[1], r[2]};
   const double j1[3] = {r[3], r[4], r[5]};
   NewState n;
   n.acc = make_double4(a1[0], a1[1], a1[2], r[6]);
   n.jrk = make_double4(j1[0], j1[1], j1[2], 0.0);
-  if (MODE == MODE_INIT) {
-    const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
-    const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
-    double dt0 = g.dt_max;
-    if (sa > 0.0 && sj > 0.0) dt0 = g.eta * 0.0625 * sqrt(sa / sj);
-    if (dt0 > 0.03125) dt0 = 0.03125;
-    if (dt0 > g.dt_max) dt0 = g.dt_max;
-    double dd = pow2floor(dt0);
-    if (dd < g.dt_min) dd = g.dt_min;
-    n.dt = dd;
-    n.t = 0.0;
-    if (!DIST) {  // positions and velocities are untouched
-      g.acc[i] = n.acc; g.jrk[i] = n.jrk; g.dt[i] = n.dt; g.t[i] = n.t;
-    } else {
-      n.pos = g.pos[i];
-      n.vel = g.vel[i];
-      store_state<true>(g, i, n, step_id);
-    }
-    return;
-  }
-  const double4 a0v = g.acc[i], j0v = g.jrk[i];
-  const double4 xpv = g.jpos[g.i0 + i], vpv = g.jvel[g.i0 + i];
-  const double ti = g.t[i], dti = g.dt[i];
+  const double4 a0v = in.a0, j0v = in.j0;
+  const double4 xpv = in.xp, vpv = in.vp;
+  const double ti = in.t, dti = in.dt;
   const double s = (MODE == MODE_STEP) ? dti : (tn - ti);
   const double a0[3] = {a0v.x, a0v.y, a0v.z}, j0[3] = {j0v.x, j0v.y, j0v.z};
   const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
@@ -228,7 +295,7 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, co
     nd = dti;
     if (dtA < dti) {
       if (0.5 * dti >= g.dt_min) nd = 0.5 * dti;
-    } else if (dtA >= 2.0 * dti && 2.0 * dti <= g.hdr->D) {
+    } else if (dtA >= 2.0 * dti && 2.0 * dti <= Dmax) {
       const double q = tn / (2.0 * dti);
       if (q == floor(q)) nd = 2.0 * dti;
     }
@@ -242,6 +309,49 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, co
   n.t = tn;
   n.dt = nd;
   store_state<DIST>(g, i, n, step_id);
+}
+
+// one active slot of the list: raw output, initial timestep, or the corrector on the particle's global records
+template <int MODE, bool DIST>
+__device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, const int slot, const double r[7],
+                                           unsigned long long &c_bits, const unsigned long long step_id) {
+  if (MODE == MODE_RAW) {
+    g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
+    g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
+    return;
+  }
+  const int i = g.list[slot];
+  if (MODE == MODE_INIT) {
+    const double a1[3] = {r[0], r[1], r[2]};
+    const double j1[3] = {r[3], r[4], r[5]};
+    NewState n;
+    n.acc = make_double4(a1[0], a1[1], a1[2], r[6]);
+    n.jrk = make_double4(j1[0], j1[1], j1[2], 0.0);
+    const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
+    double dt0 = g.dt_max;
+    if (sa > 0.0 && sj > 0.0) dt0 = g.eta * 0.0625 * sqrt(sa / sj);
+    if (dt0 > 0.03125) dt0 = 0.03125;
+    if (dt0 > g.dt_max) dt0 = g.dt_max;
+    double dd = pow2floor(dt0);
+    if (dd < g.dt_min) dd = g.dt_min;
+    n.dt = dd;
+    n.t = 0.0;
+    if (!DIST) {  // positions and velocities are untouched
+      g.acc[i] = n.acc; g.jrk[i] = n.jrk; g.dt[i] = n.dt; g.t[i] = n.t;
+    } else {
+      n.pos = g.pos[i];
+      n.vel = g.vel[i];
+      store_state<true>(g, i, n, step_id);
+    }
+    return;
+  }
+  SlotIn in;
+  in.i = i;
+  in.a0 = g.acc[i]; in.j0 = g.jrk[i];
+  in.xp = g.jpos[g.i0 + i]; in.vp = g.jvel[g.i0 + i];
+  in.t = g.t[i]; in.dt = g.dt[i];
+  correct_slot<MODE, DIST>(g, tn, in, r, c_bits, step_id, g.hdr->D);
 }
 
 // Reduction of the j-chunk partials in a FIXED order, then the corrector.

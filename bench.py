@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (scaling sweeps at N=1e6)")
     ap.add_argument("--dist-mode", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory exchange or NCCL all-gather")
     ap.add_argument("--split-min", type=int, default=0, help="peer-memory mode: exchange only blocks of at least this many active particles (0 = auto)")
+    ap.add_argument("--fuse-max", type=int, default=-1, help="loop kernels: largest block on the fused small-step path (0 = off, -1 = library default)")
     ap.add_argument("--step-mode", type=int, default=0, choices=[0, 1], help="1 GPU: 0 = CUDA graph (default), 1 = persistent loop kernel")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     return ap.parse_args()
@@ -282,6 +283,7 @@ def main():
     pkg = importlib.import_module("26al-nbody_b200")
     ctx = pkg.Context(local)
     ctx.set_step_mode(args.step_mode)
+    ctx.set_fuse_max(args.fuse_max)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pkg.dist.init_context(ctx, rank, world, device="cuda", mode=args.dist_mode, split_min=args.split_min)

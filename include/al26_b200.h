@@ -157,6 +157,19 @@ int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_p
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).
  * Bit-identical results; measured on B200 the graph is 2 % (N=1e5) to 9 % (N=1e4) faster per block step. */
 int al26_set_step_mode(al26_ctx *ctx, int mode);
+/* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
+ * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
+ * else off) take the fused small-step path
+ * -- one grid barrier instead of three, force from the CTA's own shared-memory chunk, the last CTA corrects.
+ * Available when every CTA's share of the particles fits its stage buffers (N <= ~2.2e5 on B200). */
+int al26_set_fuse_max(al26_ctx *ctx, int n_act_max);
+/* diagnostic: block steps taken through the fused path since the last commit */
+int al26_grav_fused_steps(al26_ctx *ctx, int64_t *n_fused);
+/* diagnostic, non-zero only in a library built with -DAL26_FUSE_TIMING: nanoseconds (globaltimer) CTA 0 spent, summed
+ * over the fused steps since the last commit, in [0] force + partial store + arrival, [1] waiting for all partials,
+ * [2] reduce + corrector, [4] waiting for the release counter, [5] the whole fused part; over all loop steps:
+ * [6] scan, [7] barrier (16 values) */
+int al26_grav_fuse_profile(al26_ctx *ctx, int64_t *ns16);
 /* diagnostic: number of block steps by floor(log2(n_active)) since the last commit (32 bins) */
 int al26_grav_block_histogram(al26_ctx *ctx, int64_t *hist32);
 /* diagnostic: SM cycles CTA 0 of the persistent loop kernel spent in predict / barrier / force / barrier /

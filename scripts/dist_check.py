@@ -14,6 +14,7 @@ from oracle import hermite as H
 from oracle import enrich_oracle as eo
 
 ctx = pkg.Context(local)
+ctx.set_fuse_max(int(os.environ.get("AL26_FUSE_MAX", "-1")))
 MODE = os.environ.get("AL26_DIST_MODE", "p2p")
 pkg.dist.init_context(ctx, rank, world, device="cuda", mode=MODE, split_min=int(os.environ.get("AL26_SPLIT_MIN", "0")))
 

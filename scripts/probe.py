@@ -37,18 +37,27 @@ if os.environ.get("PROBE_DECOMP"):
     ctx.set_decomposition()
     sys.exit(0)
 if os.environ.get("PROBE_LATENCY"):
-    for n in (1000, 10000, 100000):
+    sizes = [int(a) for a in os.environ.get("PROBE_SIZES", "1000,10000,100000").split(",")]
+    combos = [tuple(int(b) for b in a.split(":")) for a in os.environ.get("PROBE_COMBOS", "1:32,1:8,1:0,0:0").split(",")]
+    for n in sizes:
         c = pkg.ic.cluster(n, seed=0)
-        for mode in (1, 0):
+        for mode, fuse in combos:
             ctx.set_step_mode(mode)
+            ctx.set_fuse_max(fuse)
             g = pkg.GravityCore(ctx=ctx)
             g.set_time(0.0)
             g.commit(*[c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")])
             g.evolve(2.0 ** -9)
             steps, pairs = g.evolve(2.0 ** -9 + 2.0 ** -5)
             ms, _ = g.last_device_ms()
-            print(f"N={n} mode={'loop' if mode else 'graph'}: {steps} steps, {ms*1e3/steps:.2f} us/step, {pairs/ms*1e-6:.1f} Gpairs/s", flush=True)
+            nf = ctx.fused_steps()
+            print(f"N={n} mode={'loop' if mode else 'graph'} fuse_max={fuse}: {steps} steps, {ms*1e3/steps:.2f} us/step, {pairs/ms*1e-6:.1f} Gpairs/s, fused {nf}", flush=True)
+            if mode and nf:
+                tot = max(sum(ctx.block_histogram()), 1)
+                pr = ctx.fuse_profile()
+                print("    ns per step: " + ", ".join(f"{k} {v / (tot if k in ('scan', 'barrier') else nf):.0f}" for k, v in pr.items()), flush=True)
     ctx.set_step_mode(0)
+    ctx.set_fuse_max(-1)
     sys.exit(0)
 if os.environ.get("PROBE_BIGBLOCK"):
     n = 100000

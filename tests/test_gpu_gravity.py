@@ -22,14 +22,18 @@ def make(pkg, n, seed, model="plummer"):
     return [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
 
 
-@pytest.fixture(params=[1, 0], ids=["loop", "graph"])
+@pytest.fixture(params=[(1, 32), (1, 0), (0, 32)], ids=["loop-fused", "loop", "graph"])
 def grav(pkg, ctx, request):
-    """Both ways of driving block steps: the persistent cooperative loop kernel and the CUDA graph."""
-    ctx.set_step_mode(request.param)
+    """The ways of driving block steps: the persistent cooperative loop kernel with and without its fused
+    small-step path, and the CUDA graph."""
+    mode, fuse = request.param
+    ctx.set_step_mode(mode)
+    ctx.set_fuse_max(fuse)
     g = pkg.GravityCore(ctx=ctx)  # the session shares one context: reset its clock and parameters
     g.set_time(0.0)
     yield g
     ctx.set_step_mode(0)
+    ctx.set_fuse_max(-1)
 
 
 @pytest.mark.parametrize("n", [2, 3, 33, 257, 1000, 4096])
@@ -144,6 +148,34 @@ def test_evolve_matches_oracle_counts_and_energy(pkg, grav):
     ok1, ou1, _ = o.energies()
     de_g, de_o = ((k0 + u0) - (k1 + u1)) / (k1 + u1), ((ok0 + ou0) - (ok1 + ou1)) / (ok1 + ou1)
     assert abs(de_g) < 1e-5 and abs(de_g) <= 2.0 * abs(de_o) + 1e-9  # dE/E no worse than the CPU path
+
+
+def test_fused_small_steps_are_taken_and_agree(pkg, ctx):
+    """Loop kernel: small block steps go through the fused path (one barrier, last CTA corrects); the
+    trajectory agrees with the three-barrier path to rounding and the integer work is identical."""
+    n = 2000
+    p = make(pkg, n, seed=11)
+    out = {}
+    ctx.set_step_mode(1)
+    try:
+        for fuse in (32, 8, 0):
+            ctx.set_fuse_max(fuse)
+            g = pkg.GravityCore(ctx=ctx)
+            g.set_time(0.0)
+            g.commit(*p)
+            steps, pairs = g.evolve(0.03125)
+            h = ctx.block_histogram()
+            out[fuse] = (steps, pairs, g.get_state(), g.get_timesteps()[1], ctx.fused_steps(), sum(h[:5]), sum(h[:6]))
+    finally:
+        ctx.set_step_mode(0)
+        ctx.set_fuse_max(-1)
+    assert out[0][4] == 0 and out[32][4] > 0 and 0 < out[8][4] <= out[32][4]
+    assert out[32][5] <= out[32][4] <= out[32][6]  # every block of < 32 particles (log2 bins 0-4), plus n_act == 32
+    for fuse in (32, 8):
+        assert out[fuse][:2] == out[0][:2]
+        assert np.array_equal(out[fuse][3], out[0][3])
+        a, b = out[fuse][2], out[0][2]
+        assert vec_rel(a[1:4], b[1:4]) < 1e-11 and vec_rel(a[4:7], b[4:7]) < 1e-11
 
 
 def test_set_mass_and_time_setter(pkg, grav):
