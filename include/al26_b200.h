@@ -155,7 +155,9 @@ int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_p
 /* tuning hook: how block steps are driven on one GPU.  0 (default): a CUDA graph of three kernels per block
  * step, relaunched until the device reports the call done; 1: one persistent cooperative kernel runs the
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).
- * Bit-identical results; measured on B200 the graph is 2 % (N=1e5) to 9 % (N=1e4) faster per block step. */
+ * Bit-identical results (except the loop kernel's fused small steps, al26_set_fuse_max: identical integer work,
+ * positions to rounding); measured on B200 the graph is 3 % (N=1e5) faster, the loop with fused steps 3-7 % faster at
+ * N = 3e3..1e4, per block step. */
 int al26_set_step_mode(al26_ctx *ctx, int mode);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
