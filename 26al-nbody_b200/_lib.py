@@ -72,6 +72,7 @@ SIGNATURES = {
     "al26_set_big_block": (C.c_int, [_VP, C.c_int]),
     "al26_set_decomposition": (C.c_int, [_VP, C.c_int, C.c_double]),
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_grav_engine_steps": (C.c_int, [_VP, _PI64, C.POINTER(C.c_int)]),
     "al26_set_fuse_max": (C.c_int, [_VP, C.c_int]),
     "al26_grav_fused_steps": (C.c_int, [_VP, _PI64]),
     "al26_grav_fuse_profile": (C.c_int, [_VP, _PI64]),
@@ -192,6 +193,12 @@ class Context:
 
     def set_step_mode(self, mode):
         self.chk(self.L.al26_set_step_mode(self.h, int(mode)))
+
+    def engine_steps(self):
+        """(block steps taken by the cluster engine since the last commit, its cluster size or 0)"""
+        n, cs = C.c_int64(0), C.c_int(0)
+        self.chk(self.L.al26_grav_engine_steps(self.h, C.byref(n), C.byref(cs)))
+        return n.value, cs.value
 
     def set_fuse_max(self, n_act_max):
         """loop kernels: largest block that takes the fused small-step path (0 = off); before commit"""

@@ -41,6 +41,7 @@ struct GravHeader {
   int pad3;
   long long loop_cycles[6];  // diagnostic: CTA 0's SM cycles in predict / barrier / force / barrier / correct / barrier
   long long n_fused;             // diagnostic: block steps taken through the fused path, since the last commit
+  long long n_engine;            // diagnostic: block steps taken by the cluster engine, since the last commit
   long long fuse_ns[16];         // diagnostic (builds with -DAL26_FUSE_TIMING only): globaltimer ns per fused-step segment
 };
 
@@ -125,6 +126,13 @@ struct GravDev {
   int split_min;   // block steps with fewer active particles are computed redundantly by every rank (no exchange)
   void *slab[MAX_PEERS];  // slab[q]: rank q's staging slab as mapped in this process (slab[rank] = own)
 };
+
+// ---- the cluster engine (hermite_engine.cu): runs of small block steps for small N inside one thread-block cluster
+constexpr int ENG_MAX_ACT = 32;  // largest block the engine steps itself
+constexpr int ENG_CS_MAX = 16;   // cluster size: 8 (portable) or 16
+int engine_smem_bytes(int p_cap);
+cudaError_t engine_kernel_setup(int max_smem_optin);
+bool engine_fits(int cs, int p_cap, int max_smem_optin);
 
 // ---- work decomposition of one force evaluation, a pure function of (n_act, n_tot, grid) so
 // the force kernel and the reduce/corrector kernel agree without communicating ----
@@ -227,6 +235,7 @@ int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cuda
 int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsigned long long step_id0,
                      cudaStream_t s, cudaError_t *err);
 int launch_pull(const GravDev &g, unsigned long long step_id, cudaStream_t s);
+int launch_engine(const GravDev &g, int phase, int cs, int p_cap, cudaStream_t s, cudaError_t *err);
 cudaError_t loop_kernel_setup();
 int loop_max_ctas_per_sm(int variant);
 

@@ -99,6 +99,10 @@ struct al26_ctx {
   double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
   int step_mode = 0;      // 1 GPU: 0 = CUDA graph of 3 kernels per block step (default, measured ~2-9 % faster), 1 = persistent cooperative loop kernel
   bool coop_ok = false;   // device supports cooperative launch
+  int max_smem_optin = 0;  // largest dynamic shared memory a block may opt in to
+  bool engine_ok = false;  // the cluster-engine kernel's attributes could be set
+  bool engine_on = false;  // this commit's graph carries the engine (step mode 2 and the particles fit one cluster)
+  int engine_cs = 0, engine_p = 0;  // its cluster size and per-CTA particle capacity
   cudaGraphExec_t graph = nullptr;
   int graph_steps = 0;
   bool graph_stale = false;  // parameters changed since the graph captured them by value
@@ -302,8 +306,29 @@ int reduce_tnext(al26_ctx *c, int phase) {
   return 0;
 }
 
+// step mode 2: does the particle set fit one cluster?  8 CTAs when that is enough, else 16.
+void decide_engine(al26_ctx *c) {
+  c->engine_on = false;
+  if (c->step_mode != 2 || c->world != 1 || !c->engine_ok || !c->committed) return;
+  const int n = c->g.n_tot;
+  for (int cs = 8; cs <= ENG_CS_MAX; cs *= 2) {
+    const int p_cap = (((n + cs - 1) / cs) + 7) & ~7;
+    if (engine_fits(cs, p_cap, c->max_smem_optin)) {
+      c->engine_on = true;
+      c->engine_cs = cs;
+      c->engine_p = p_cap;
+      return;
+    }
+  }
+}
+
 // one block step (or the init / sync variant) enqueued on the stream
-int enqueue_step(al26_ctx *c, int mode, int phase) {
+int enqueue_step(al26_ctx *c, int mode, int phase, bool with_engine = false) {
+  if (with_engine && mode == MODE_STEP && c->engine_on) {  // first every small step up to the next big one, on chip
+    cudaError_t e = cudaSuccess;
+    c->launches += launch_engine(c->g, phase, c->engine_cs, c->engine_p, c->stream, &e);
+    if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cluster-engine launch failed: %s", cudaGetErrorString(e));
+  }
   c->launches += launch_predict_list(c->g, mode, phase, c->stream);
   int rc = gather_j(c);
   if (rc) return rc;
@@ -322,12 +347,13 @@ int build_graph(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   c->graph = nullptr;
   if (is_p2p(c)) return 0;  // the peer-memory path runs entirely inside the loop kernel
+  decide_engine(c);
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   const int64_t l0 = c->launches;
   int rc = 0;
   for (int r = 0; r < GRAPH_ROUNDS && !rc; r++)
-    for (int ph = 0; ph < 3 && !rc; ph++) rc = enqueue_step(c, MODE_STEP, ph);
+    for (int ph = 0; ph < 3 && !rc; ph++) rc = enqueue_step(c, MODE_STEP, ph, true);
   c->launches = l0;
   cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
   if (rc) {
@@ -508,6 +534,9 @@ al26_ctx *al26_create(int device_id) {
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_id);
   c->coop_ok = coop != 0;
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
+  c->engine_ok = engine_kernel_setup(c->max_smem_optin) == cudaSuccess;
+  if (!c->engine_ok) cudaGetLastError();
   return c;
 }
 
@@ -809,7 +838,7 @@ int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t 
     while (true) {
       for (int b = 0; b < batch; b++) {
         CU(cudaGraphLaunch(c->graph, c->stream));
-        c->launches += 3 * c->graph_steps;
+        c->launches += (c->engine_on ? 4 : 3) * c->graph_steps;
         launches_needed++;
       }
       batch = 1;
@@ -1256,9 +1285,21 @@ int al26_grav_fuse_profile(al26_ctx *c, int64_t *ns8) {  // 16 values
 
 int al26_set_step_mode(al26_ctx *c, int mode) {
   if (!c) return AL26_EINVAL;
-  if (mode != 0 && mode != 1) return fail(c, AL26_EINVAL, "step mode must be 0 (graph) or 1 (persistent loop)");
+  if (mode < 0 || mode > 2) return fail(c, AL26_EINVAL, "step mode must be 0 (graph), 1 (persistent loop) or 2 (graph + cluster engine)");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_step_mode during evolve");
+  if (mode != c->step_mode && (mode == 2 || c->step_mode == 2)) c->graph_stale = c->committed;  // the graph gains / loses the engine nodes
   c->step_mode = mode;
+  return 0;
+}
+
+int al26_grav_engine_steps(al26_ctx *c, int64_t *n_engine, int *cluster_size) {
+  if (!c || !n_engine) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "engine_steps before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  *n_engine = c->h_hdr->n_engine;
+  if (cluster_size) *cluster_size = c->engine_on ? c->engine_cs : 0;
   return 0;
 }
 

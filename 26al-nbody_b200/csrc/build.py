@@ -20,6 +20,7 @@ UNITS = [
     ("hermite_force.cu", ["--fmad=false"]),
     ("hermite_step.cu", ["--fmad=false"]),
     ("hermite_loop.cu", ["--fmad=false"]),
+    ("hermite_engine.cu", ["--fmad=false"]),
     ("enrich.cu", ["--fmad=false"]),
     ("analysis.cu", ["--fmad=false"]),
     ("api.cu", ["--fmad=false"]),

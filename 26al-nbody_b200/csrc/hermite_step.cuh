@@ -261,7 +261,7 @@ struct SlotIn {
 template <int MODE, bool DIST>
 __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, const SlotIn &in, const double r[7],
                                              unsigned long long &c_bits, const unsigned long long step_id,
-                                             const double Dmax) {
+                                             const double Dmax, NewState *out = nullptr) {
   const int i = in.i;
   const double a1[3] = {r[0], r[1], r[2]};
   const double j1[3] = {r[3], r[4], r[5]};
@@ -309,6 +309,7 @@ __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, 
   n.t = tn;
   n.dt = nd;
   store_state<DIST>(g, i, n, step_id);
+  if (out) *out = n;
 }
 
 // one active slot of the list: raw output, initial timestep, or the corrector on the particle's global records

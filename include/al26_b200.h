@@ -159,6 +159,15 @@ int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_p
  * positions to rounding); measured on B200 the graph is 3 % (N=1e5) faster, the loop with fused steps 3-7 % faster at
  * N = 3e3..1e4, per block step. */
 int al26_set_step_mode(al26_ctx *ctx, int mode);
+/* step mode 2 = the graph with the CLUSTER ENGINE in front of every block step: one thread-block cluster (8 or 16
+ * CTAs, one per SM) keeps the whole particle set in distributed shared memory and takes every run of small block
+ * steps (<= 32 active particles) on chip -- DSMEM hops and hardware cluster barriers (~0.1-0.2 us) instead of L2
+ * round trips, atomics and fences (~0.4 us each) -- writing corrected particles through to the global records; a
+ * bigger block is left to the grid-wide kernels that follow in the graph.  Applies when the particles fit one
+ * cluster (N <= ~14000 on B200; otherwise the mode behaves like 0).  Identical integer work, positions to rounding.
+ * diagnostic: block steps the engine took since the last commit, and its cluster size (0 = engine not in use;
+ * cluster_size may be NULL) */
+int al26_grav_engine_steps(al26_ctx *ctx, int64_t *n_engine, int *cluster_size);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
  * else off) take the fused small-step path

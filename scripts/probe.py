@@ -51,7 +51,11 @@ if os.environ.get("PROBE_LATENCY"):
             steps, pairs = g.evolve(2.0 ** -9 + 2.0 ** -5)
             ms, _ = g.last_device_ms()
             nf = ctx.fused_steps()
-            print(f"N={n} mode={'loop' if mode else 'graph'} fuse_max={fuse}: {steps} steps, {ms*1e3/steps:.2f} us/step, {pairs/ms*1e-6:.1f} Gpairs/s, fused {nf}", flush=True)
+            ne, cs = ctx.engine_steps()
+            print(f"N={n} mode={('graph', 'loop', 'graph+engine')[mode]} fuse_max={fuse}: {steps} steps, {ms*1e3/steps:.2f} us/step, {pairs/ms*1e-6:.1f} Gpairs/s, fused {nf}, engine {ne} (cluster {cs})", flush=True)
+            if mode == 2 and ne:
+                pr = ctx.loop_profile()
+                print("    engine, CTA 0 cycles per engine step (predict+list / sync+count / force / sync / correct+min / sync): " + ", ".join(f"{v / ne:.0f}" for v in pr.values()), flush=True)
             if mode and nf:
                 tot = max(sum(ctx.block_histogram()), 1)
                 pr = ctx.fuse_profile()

@@ -22,10 +22,10 @@ def make(pkg, n, seed, model="plummer"):
     return [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
 
 
-@pytest.fixture(params=[(1, 32), (1, 0), (0, 32)], ids=["loop-fused", "loop", "graph"])
+@pytest.fixture(params=[(1, 32), (1, 0), (0, 32), (2, 32)], ids=["loop-fused", "loop", "graph", "engine"])
 def grav(pkg, ctx, request):
     """The ways of driving block steps: the persistent cooperative loop kernel with and without its fused
-    small-step path, and the CUDA graph."""
+    small-step path, the CUDA graph, and the graph with the cluster engine in front of every block step."""
     mode, fuse = request.param
     ctx.set_step_mode(mode)
     ctx.set_fuse_max(fuse)
@@ -176,6 +176,36 @@ def test_fused_small_steps_are_taken_and_agree(pkg, ctx):
         assert np.array_equal(out[fuse][3], out[0][3])
         a, b = out[fuse][2], out[0][2]
         assert vec_rel(a[1:4], b[1:4]) < 1e-11 and vec_rel(a[4:7], b[4:7]) < 1e-11
+
+
+@pytest.mark.parametrize("n,model", [(1000, "plummer"), (3000, "fractal"), (10000, "plummer")])
+def test_cluster_engine_takes_the_small_steps_and_agrees(pkg, ctx, n, model):
+    """Step mode 2: the runs of small block steps are taken on chip by one thread-block cluster (8 CTAs, or 16 when
+    the particles need them); identical integer work, trajectory to rounding, same energy error."""
+    p = make(pkg, n, seed=5, model=model)
+    out = {}
+    try:
+        for mode in (2, 0):
+            ctx.set_step_mode(mode)
+            g = pkg.GravityCore(ctx=ctx, eps2=1e-6 if model == "fractal" else 0.0)
+            g.set_time(0.0)
+            g.commit(*p)
+            e0 = sum(g.energies()[:2])
+            work = [g.evolve(0.0078125 * k) for k in range(1, 4)]  # the engine restarts with every call
+            h = ctx.block_histogram()
+            out[mode] = dict(work=work, state=g.get_state(), dt=g.get_timesteps()[1], hist=h, eng=ctx.engine_steps(),
+                             de=(e0 - sum(g.energies()[:2])) / e0)
+    finally:
+        ctx.set_step_mode(0)
+    n_eng, cs = out[2]["eng"]
+    assert cs == (8 if n <= 7000 else 16) and out[0]["eng"] == (0, 0)
+    small = sum(out[2]["hist"][:5])  # blocks of < 32 particles (log2 bins 0-4)
+    assert small <= n_eng <= sum(out[2]["hist"][:6]) and n_eng > 0
+    assert out[2]["work"] == out[0]["work"] and out[2]["hist"] == out[0]["hist"]
+    assert np.array_equal(out[2]["dt"], out[0]["dt"])
+    a, b = out[2]["state"], out[0]["state"]
+    assert vec_rel(a[1:4], b[1:4]) < 1e-10 and vec_rel(a[4:7], b[4:7]) < 1e-10
+    assert abs(out[2]["de"] - out[0]["de"]) < 1e-9 + 1e-3 * abs(out[0]["de"])
 
 
 def test_set_mass_and_time_setter(pkg, grav):
