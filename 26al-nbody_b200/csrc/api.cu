@@ -659,6 +659,8 @@ int al26_grav_set_params(al26_ctx *c, double eps2, double eta, double dt_max, do
   if (!(eps2 >= 0.0) || !(eta > 0.0) || !(dt_max > 0.0) || !(dt_min > 0.0) || dt_min > dt_max)
     return fail(c, AL26_EINVAL, "bad gravity parameters eps2=%g eta=%g dt_max=%g dt_min=%g", eps2, eta, dt_max, dt_min);
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_params during evolve");
+  if (dt_min < 4.909093465297727e-91 /* 2^-300 */)
+    return fail(c, AL26_EINVAL, "dt_min %g below 2^-300 (the corrector forms dt^-3)", dt_min);
   c->eps2 = eps2;
   c->eta = eta;
   c->dt_max = pow2floor_h(dt_max);
@@ -1002,6 +1004,9 @@ int al26_grav_set_timesteps(al26_ctx *c, int64_t n, const double *t, const doubl
   if (!c) return AL26_EINVAL;
   if (!c->committed) return fail(c, AL26_ESTATE, "set_timesteps before commit");
   if (n != c->n_tot || !t || !dt) return fail(c, AL26_EINVAL, "set_timesteps: size mismatch");
+  for (int64_t i = 0; i < n; i++)  // the block-step machinery relies on it (exact dyadic times, exponent-flip reciprocals)
+    if (!(dt[i] >= 4.909093465297727e-91) || !(dt[i] <= 1.0e300) || dt[i] != pow2floor_h(dt[i]))
+      return fail(c, AL26_EINVAL, "set_timesteps: dt[%lld] = %.17g is not a power of two", (long long)i, dt[i]);
   CU(cudaSetDevice(c->device));
   const GravDev &g = c->g;
   CU(cudaMemcpyAsync(g.t, t + g.i0, (size_t)g.n_loc * sizeof(double), cudaMemcpyHostToDevice, c->stream));

@@ -276,7 +276,18 @@ __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, 
   const double xp[3] = {xpv.x, xpv.y, xpv.z}, vp[3] = {vpv.x, vpv.y, vpv.z};
   double x1[3], v1[3], a2[3], a3[3];
   const double s2 = s * s;
-  const double is2 = 1.0 / s2, is3 = 1.0 / (s2 * s);
+  // 1/s^2, 1/s^3: in a block step s is a power of two (>= dt_min = 2^-40 by default), so the reciprocal is an exponent
+  // flip and the powers are exact products -- bit-identical to the oracle's divisions (a quotient by an exact power of
+  // two is exact), without three divisions in the step's dependent chain
+  double is1 = 0.0, is2, is3;
+  if (MODE == MODE_STEP) {
+    is1 = __longlong_as_double(0x7FE0000000000000ll - __double_as_longlong(s));
+    is2 = is1 * is1;
+    is3 = is2 * is1;
+  } else {
+    is2 = 1.0 / s2;
+    is3 = 1.0 / (s2 * s);
+  }
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     const double da = a0[c] - a1[c];
@@ -296,7 +307,7 @@ __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, 
     if (dtA < dti) {
       if (0.5 * dti >= g.dt_min) nd = 0.5 * dti;
     } else if (dtA >= 2.0 * dti && 2.0 * dti <= Dmax) {
-      const double q = tn / (2.0 * dti);
+      const double q = tn * (0.5 * is1);  // == tn / (2 dt), exactly
       if (q == floor(q)) nd = 2.0 * dti;
     }
     const unsigned long long cb = dbits(tn + nd);
