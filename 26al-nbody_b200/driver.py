@@ -146,13 +146,16 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
 
 def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, max_outer_steps=None, verbose=False,
         device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None,
-        epsilon=None, progress=None):
-    """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200"."""
+        epsilon=None, progress=None, step_mode=None):
+    """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200".
+    step_mode: None = library default (CUDA graph); 2 = graph + cluster engine (small N, see include/al26_b200.h)."""
     from .gravity import B200Gravity
     from .gravity import GravityCore
     from . import _lib
     stellar = stellar or StellarStub()
     ctx = _lib.Context(device)
+    if step_mode is not None:
+        ctx.set_step_mode(step_mode)
     pot = None
     if model == "fractal" and nstars > 2000:
         def pot(m, x, y, z):  # the fractal generator's virial scaling needs U: use the device pair reduction

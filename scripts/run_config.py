@@ -18,14 +18,16 @@ def progress(k, info):
     if k % 50 == 0:
         print(f"outer step {k}: t = {info['t_new_myr']:.2f} Myr, {time.perf_counter() - t0:.1f} s, "
               f"{info['block_steps']} block steps, r_vir {info['virial_radius_pc']:.3f} pc", file=sys.stderr, flush=True)
+step_mode = int(os.environ["AL26_STEP_MODE"]) if "AL26_STEP_MODE" in os.environ else None  # 2 = graph + cluster engine
 cluster, gravity, stellar, enrich, hist = pkg.driver.run(seed=1, max_outer_steps=steps, log=events.append, progress=progress,
-                                                         yields_file=f"gpurun_out/config{cfg}", **kw)
+                                                         yields_file=f"gpurun_out/config{cfg}", step_mode=step_mode, **kw)
+eng_steps, eng_cs = gravity._core.ctx.engine_steps()
 wall = time.perf_counter() - t0
 tm = {k: float(sum(h["timings"][k] for h in hist)) for k in ("grav", "stel", "copy", "discs", "step")}
 inv, fin, alive, kicked = enrich.get()
 R = pkg.ROW
 lm = (cluster.mass.value_in(U.MSun) <= 3.0)
-print(json.dumps({"config": cfg, **{k: (str(v) if not isinstance(v, (int, str)) else v) for k, v in kw.items()},
+print(json.dumps({"config": cfg, "step_mode": step_mode, "engine_cluster_size": eng_cs, **{k: (str(v) if not isinstance(v, (int, str)) else v) for k, v in kw.items()},
                   "outer_steps": len(hist), "t_end_myr": hist[-1]["t_new_myr"], "wall_s": wall, "phase_seconds": tm,
                   "block_steps": int(sum(h["block_steps"] for h in hist)), "pairs": float(sum(h["pairs"] for h in hist)),
                   "sn_events": int(sum(len(h["sn_events"]) for h in hist)), "discs_condensed": int((~alive).sum()),
