@@ -97,7 +97,7 @@ struct al26_ctx {
   int max_rounds = FORCE_MAX_ROUNDS;      // tuning: work items per CTA at most
   int fuse_max = -1;                      // loop kernels: block steps of at most this many particles take the fused path (0 = off, -1 = by N)
   double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
-  int step_mode = 0;      // 1 GPU: 0 = CUDA graph of 3 kernels per block step (default, measured ~2-9 % faster), 1 = persistent cooperative loop kernel
+  int step_mode = -1;     // 1 GPU: -1 = automatic (2 when the particles fit one cluster, else 0), 0 = CUDA graph of 3 kernels per block step, 1 = persistent cooperative loop kernel, 2 = graph + cluster engine
   bool coop_ok = false;   // device supports cooperative launch
   int max_smem_optin = 0;  // largest dynamic shared memory a block may opt in to
   bool engine_ok = false;  // the cluster-engine kernel's attributes could be set
@@ -309,7 +309,7 @@ int reduce_tnext(al26_ctx *c, int phase) {
 // step mode 2: does the particle set fit one cluster?  8 CTAs when that is enough, else 16.
 void decide_engine(al26_ctx *c) {
   c->engine_on = false;
-  if (c->step_mode != 2 || c->world != 1 || !c->engine_ok || !c->committed) return;
+  if ((c->step_mode != 2 && c->step_mode != -1) || c->world != 1 || !c->engine_ok || !c->committed) return;
   const int n = c->g.n_tot;
   for (int cs = 8; cs <= ENG_CS_MAX; cs *= 2) {
     const int p_cap = (((n + cs - 1) / cs) + 7) & ~7;
@@ -1290,9 +1290,10 @@ int al26_grav_fuse_profile(al26_ctx *c, int64_t *ns8) {  // 16 values
 
 int al26_set_step_mode(al26_ctx *c, int mode) {
   if (!c) return AL26_EINVAL;
-  if (mode < 0 || mode > 2) return fail(c, AL26_EINVAL, "step mode must be 0 (graph), 1 (persistent loop) or 2 (graph + cluster engine)");
+  if (mode < -1 || mode > 2)
+    return fail(c, AL26_EINVAL, "step mode must be -1 (automatic), 0 (graph), 1 (persistent loop) or 2 (graph + cluster engine)");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_step_mode during evolve");
-  if (mode != c->step_mode && (mode == 2 || c->step_mode == 2)) c->graph_stale = c->committed;  // the graph gains / loses the engine nodes
+  if (mode != c->step_mode) c->graph_stale = c->committed;  // the graph may gain / lose the engine nodes
   c->step_mode = mode;
   return 0;
 }

@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--dist-mode", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory exchange or NCCL all-gather")
     ap.add_argument("--split-min", type=int, default=0, help="peer-memory mode: exchange only blocks of at least this many active particles (0 = auto)")
     ap.add_argument("--fuse-max", type=int, default=-1, help="loop kernels: largest block on the fused small-step path (0 = off, -1 = library default)")
-    ap.add_argument("--step-mode", type=int, default=0, choices=[0, 1], help="1 GPU: 0 = CUDA graph (default), 1 = persistent loop kernel")
+    ap.add_argument("--step-mode", type=int, default=-1, choices=[-1, 0, 1, 2], help="1 GPU: -1 = library default (graph; + cluster engine when N fits one cluster), 0 = CUDA graph, 1 = persistent loop kernel, 2 = graph + cluster engine")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     return ap.parse_args()
 

@@ -60,7 +60,7 @@ if os.environ.get("PROBE_LATENCY"):
                 tot = max(sum(ctx.block_histogram()), 1)
                 pr = ctx.fuse_profile()
                 print("    ns per step: " + ", ".join(f"{k} {v / (tot if k in ('scan', 'barrier') else nf):.0f}" for k, v in pr.items()), flush=True)
-    ctx.set_step_mode(0)
+    ctx.set_step_mode(-1)
     ctx.set_fuse_max(-1)
     sys.exit(0)
 if os.environ.get("PROBE_BIGBLOCK"):

@@ -32,7 +32,7 @@ def grav(pkg, ctx, request):
     g = pkg.GravityCore(ctx=ctx)  # the session shares one context: reset its clock and parameters
     g.set_time(0.0)
     yield g
-    ctx.set_step_mode(0)
+    ctx.set_step_mode(-1)
     ctx.set_fuse_max(-1)
 
 
@@ -167,7 +167,7 @@ def test_fused_small_steps_are_taken_and_agree(pkg, ctx):
             h = ctx.block_histogram()
             out[fuse] = (steps, pairs, g.get_state(), g.get_timesteps()[1], ctx.fused_steps(), sum(h[:5]), sum(h[:6]))
     finally:
-        ctx.set_step_mode(0)
+        ctx.set_step_mode(-1)
         ctx.set_fuse_max(-1)
     assert out[0][4] == 0 and out[32][4] > 0 and 0 < out[8][4] <= out[32][4]
     assert out[32][5] <= out[32][4] <= out[32][6]  # every block of < 32 particles (log2 bins 0-4), plus n_act == 32
@@ -196,7 +196,7 @@ def test_cluster_engine_takes_the_small_steps_and_agrees(pkg, ctx, n, model):
             out[mode] = dict(work=work, state=g.get_state(), dt=g.get_timesteps()[1], hist=h, eng=ctx.engine_steps(),
                              de=(e0 - sum(g.energies()[:2])) / e0)
     finally:
-        ctx.set_step_mode(0)
+        ctx.set_step_mode(-1)
     n_eng, cs = out[2]["eng"]
     assert cs == (8 if n <= 7000 else 16) and out[0]["eng"] == (0, 0)
     small = sum(out[2]["hist"][:5])  # blocks of < 32 particles (log2 bins 0-4)
