@@ -145,27 +145,38 @@ __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const 
     }
     __syncthreads();
     if (is_lm) {
+      // Sources in groups of 64: the hot loop only MARKS the sources whose local bubble holds this disc (a predicated
+      // integer OR) -- their deposit, 6 DP instructions that predication would otherwise issue for every pair, is
+      // added afterwards for the marked ones only (rare: R = 0.1 pc in a ~1 pc cluster), still in ascending source
+      // order, so the sums keep the reference's rounding.
+      for (int k0 = 0; k0 < cnt; k0 += 64) {
+        const int gn = min(64, cnt - k0);
+        unsigned long long marked = 0ull;
 #pragma unroll 4
-      for (int k = 0; k < cnt; k++) {
-        const double4 A = sa[k];
-        const double4 B = sb[k];
-        // global model: distance_limit == 0 -> no test (:688)
-        g26 += (A.w * eta_g) * p.dt_s;
-        g60 += (B.x * eta_g) * p.dt_s;
-        // local model: skip when bubble_radius <= d_sep (:689-691); q_local is the exact
-        // d^2 threshold of that test, so no sqrt is needed here
-        const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        if (!(d2 >= p.q_local)) {
-          l26 += (A.w * eta_l) * p.dt_s;
-          l60 += (B.x * eta_l) * p.dt_s;
+        for (int kk = 0; kk < gn; kk++) {
+          const double4 A = sa[k0 + kk];
+          const double4 B = sb[k0 + kk];
+          // global model: distance_limit == 0 -> no test (:688)
+          g26 += (A.w * eta_g) * p.dt_s;
+          g60 += (B.x * eta_g) * p.dt_s;
+          // local model: skip when bubble_radius <= d_sep (:689-691); q_local is the exact
+          // d^2 threshold of that test, so no sqrt is needed here
+          const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+          const double d2 = dx * dx + dy * dy + dz * dz;
+          if (!(d2 >= p.q_local)) marked |= 1ull << kk;
+          if (n_ev > 0 && B.w != 0.0) {
+            // calc_star_distance + calc_eta_disk_sne (:1331-1333)
+            const double d = sqrt(d2);
+            const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
+            s26 += B.y * eta;
+            s60 += B.z * eta;
+          }
         }
-        if (n_ev > 0 && B.w != 0.0) {
-          // calc_star_distance + calc_eta_disk_sne (:1331-1333)
-          const double d = sqrt(d2);
-          const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
-          s26 += B.y * eta;
-          s60 += B.z * eta;
+        while (marked) {
+          const int kk = __ffsll((long long)marked) - 1;
+          marked &= marked - 1ull;
+          l26 += (sa[k0 + kk].w * eta_l) * p.dt_s;
+          l60 += (sb[k0 + kk].x * eta_l) * p.dt_s;
         }
       }
     }
