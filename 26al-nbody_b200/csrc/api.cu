@@ -342,6 +342,9 @@ int enqueue_step(al26_ctx *c, int mode, int phase, bool with_engine = false) {
 }
 
 constexpr int GRAPH_ROUNDS = 8;  // 3 phases x 8 = 24 block steps per graph launch
+// with the cluster engine a graph slot covers a whole run of small steps plus one big step, and a call often ends
+// inside the first slots: a shorter graph leaves fewer no-op launches behind (AL26_GRAPH_ROUNDS_ENGINE overrides)
+constexpr int GRAPH_ROUNDS_ENGINE = 2;
 
 int build_graph(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
@@ -352,7 +355,12 @@ int build_graph(al26_ctx *c) {
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   const int64_t l0 = c->launches;
   int rc = 0;
-  for (int r = 0; r < GRAPH_ROUNDS && !rc; r++)
+  int rounds = GRAPH_ROUNDS;
+  if (c->engine_on) {
+    rounds = GRAPH_ROUNDS_ENGINE;
+    if (const char *e = getenv("AL26_GRAPH_ROUNDS_ENGINE")) rounds = atoi(e) > 0 ? atoi(e) : rounds;
+  }
+  for (int r = 0; r < rounds && !rc; r++)
     for (int ph = 0; ph < 3 && !rc; ph++) rc = enqueue_step(c, MODE_STEP, ph, true);
   c->launches = l0;
   cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
@@ -364,7 +372,7 @@ int build_graph(al26_ctx *c) {
   e = cudaGraphInstantiate(&c->graph, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) return fail(c, AL26_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-  c->graph_steps = 3 * GRAPH_ROUNDS;
+  c->graph_steps = 3 * rounds;
   return 0;
 }
 
