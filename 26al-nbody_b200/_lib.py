@@ -79,6 +79,7 @@ SIGNATURES = {
     "al26_grav_block_histogram": (C.c_int, [_VP, _PI64]),
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
+    "al26_bench_fp64_with_rsqrt": (C.c_int, [_VP, _PD]),
     "al26_local_densities": (C.c_int, [_VP, C.c_int64, _D, _D, _D, _D, _D]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
@@ -228,6 +229,12 @@ class Context:
     def fp64_peak_tflops(self):
         tf = C.c_double(0)
         self.chk(self.L.al26_bench_fp64_peak(self.h, C.byref(tf)))
+        return tf.value
+
+    def fp64_with_rsqrt_tflops(self):
+        """DFMA TFLOP/s left when one independent MUFU.RSQ64H rides along per 32 DFMAs (the force kernel's ratio)"""
+        tf = C.c_double(0)
+        self.chk(self.L.al26_bench_fp64_with_rsqrt(self.h, C.byref(tf)))
         return tf.value
 
     def local_densities(self, x_pc, y_pc, z_pc, mass_msun):

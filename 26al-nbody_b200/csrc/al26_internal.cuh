@@ -230,6 +230,7 @@ int force_smem_bytes();
 int force_variant_count();
 int force_variant_info(int v, int *ctas_per_sm, int *ipt);
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
+double launch_dfma_mufu_mix(int sm_count, int iters, double *scratch, cudaStream_t s);  // + 1 MUFU.RSQ64H per 32 DFMA
 cudaError_t force_kernel_setup();
 int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cudaError_t *err);
 int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsigned long long step_id0,

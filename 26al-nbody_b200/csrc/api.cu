@@ -1337,16 +1337,16 @@ int al26_grav_loop_profile(al26_ctx *c, int64_t *cycles6) {
   return 0;
 }
 
-int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {
+static int bench_fp64(al26_ctx *c, double *tflops, bool with_mufu) {
   if (!c || !tflops) return AL26_EINVAL;
   CU(cudaSetDevice(c->device));
   int rc = ensure_scratch(c, 1024);
   if (rc) return rc;
-  launch_dfma_peak(c->sm_count, 2000, c->scratch, c->stream);  // warm-up
+  (with_mufu ? launch_dfma_mufu_mix : launch_dfma_peak)(c->sm_count, 2000, c->scratch, c->stream);  // warm-up
   double best = 0.0;
   for (int r = 0; r < 5; r++) {
     CU(cudaEventRecord(c->ev0, c->stream));
-    const double flops = launch_dfma_peak(c->sm_count, 20000, c->scratch, c->stream);
+    const double flops = (with_mufu ? launch_dfma_mufu_mix : launch_dfma_peak)(c->sm_count, 20000, c->scratch, c->stream);
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaEventSynchronize(c->ev1));
     float ms = 0.f;
@@ -1359,6 +1359,9 @@ int al26_bench_fp64_peak(al26_ctx *c, double *tflops) {
   *tflops = best;
   return 0;
 }
+
+int al26_bench_fp64_peak(al26_ctx *c, double *tflops) { return bench_fp64(c, tflops, false); }
+int al26_bench_fp64_with_rsqrt(al26_ctx *c, double *tflops) { return bench_fp64(c, tflops, true); }
 
 int al26_local_densities(al26_ctx *c, int64_t n, const double *x_pc, const double *y_pc, const double *z_pc,
                          const double *mass_msun, double *rho) {

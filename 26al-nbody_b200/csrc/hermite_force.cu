@@ -77,6 +77,30 @@ __global__ void __launch_bounds__(512, 2) k_dfma_peak(double *out, int iters, do
   if (r == 123.456) out[0] = r;  // never true; keeps the chains alive
 }
 
+// the same 64 DFMAs per iteration plus two MUFU.RSQ64H (one per 32 DFMAs: the force kernel's ratio), whose
+// results feed nothing the DFMA chains wait for: does the 64-bit MUFU take FP64 issue slots?
+__global__ void __launch_bounds__(512, 2) k_dfma_mufu_mix(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  double m0 = 1.0 + threadIdx.x, m1 = 2.0 + threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      if (u == 3) asm volatile("rsqrt.approx.ftz.f64 %0, %0;" : "+d"(m0));
+      if (u == 7) asm volatile("rsqrt.approx.ftz.f64 %0, %0;" : "+d"(m1));
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7)) + (m0 + m1);
+  if (r == 123.456) out[0] = r;  // never true; keeps the chains alive
+}
+
+double launch_dfma_mufu_mix(int sm_count, int iters, double *scratch, cudaStream_t s) {
+  const int blocks = sm_count * 2, threads = 512;
+  k_dfma_mufu_mix<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9);
+  return 2.0 * (double)blocks * threads * 64.0 * (double)iters;  // DFMA flops of one launch
+}
+
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s) {
   const int blocks = sm_count * 2, threads = 512;
   k_dfma_peak<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9);

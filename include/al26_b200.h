@@ -191,6 +191,9 @@ int al26_grav_loop_profile(al26_ctx *ctx, int64_t *cycles6);
 /* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
  * the roofline denominator of the force kernel */
 int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);
+/* the same DFMA chains with one independent MUFU.RSQ64H per 32 DFMAs (the force kernel's ratio): the DFMA TFLOP/s
+ * that remain -- i.e. whether the 64-bit reciprocal square root takes FP64 issue slots */
+int al26_bench_fp64_with_rsqrt(al26_ctx *ctx, double *tflops);
 
 /* ---- post-processing ------------------------------------------------------------------
  * replaces: `local_densities_numba(x, y, z, masses)` (plotting/al26_plot.py:324-359, called by
