@@ -50,7 +50,7 @@ enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
 // ---- fused small block steps of the persistent loop kernels (hermite_loop.cu): the scheduler pass leaves every
 // active particle's predicted state and old force in this compact record, so the force phase and the correcting
 // CTA fetch everything they need in one round trip.  One buffer is enough: a step's readers all finish before
-// the step's release word is published.
+// the step's release counter is complete.
 constexpr int FUSE_CAP = 32;  // largest block handled by the fused path
 constexpr int FUSE_AUTO_MAX_N = 32768;  // automatic setting: fused path on for N <= this many particles
 struct ActBuf {

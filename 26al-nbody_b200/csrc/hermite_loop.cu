@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, c
       FT_ADD(7, fa2 - fa1);  // barrier + n_act load
     }
     if (fuse && n_act > 0 && n_act <= g.fuse_max) {
-      // ---- fused small step: force from shared memory, last CTA corrects, release word ------
+      // ---- fused small step: force from shared memory, per-slot corrector CTAs, release counter ------
       if (!fused_step<C>(g, sm, cur, nxt, n_act, CHUNK_CNT, CHUNK_PARTS, tn, g.Dmax, shr, &sh_word, -1, tnext_bits)) break;
       PROF(2)
     } else {

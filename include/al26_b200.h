@@ -173,7 +173,7 @@ int al26_grav_engine_steps(al26_ctx *ctx, int64_t *n_engine, int *cluster_size);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
  * else off) take the fused small-step path
- * -- one grid barrier instead of three, force from the CTA's own shared-memory chunk, the last CTA corrects.
+ * -- one grid barrier instead of three, force from the CTA's own shared-memory chunk, one corrector CTA per slot.
  * Available when every CTA's share of the particles fits its stage buffers (N <= ~2.2e5 on B200). */
 int al26_set_fuse_max(al26_ctx *ctx, int n_act_max);
 /* diagnostic: block steps taken through the fused path since the last commit */
