@@ -254,12 +254,34 @@ def test_error_codes_and_edge_cases(pkg, ctx):
         g.set_params(eta=-1.0)
     assert ei.value.code == -1
     assert g.evolve(0.0) == (0, 0)  # t_end == model time: nothing to do
+    # timesteps live on the dyadic ladder: the hook refuses anything else, and a floor below 2^-300
+    g.initialize()
+    t, dt = g.get_timesteps()
+    g.set_timesteps(t, dt)
+    bad = dt.copy(); bad[3] *= 1.5
+    with pytest.raises(pkg.Al26Error) as ei:
+        g.set_timesteps(t, bad)
+    assert ei.value.code == -1
+    with pytest.raises(pkg.Al26Error) as ei:
+        g.set_params(dt_min=1e-200)
+    assert ei.value.code == -1
+    with pytest.raises(pkg.Al26Error) as ei:
+        ctx.set_step_mode(3)
+    assert ei.value.code == -1
     # a single particle moves on a straight line
     g.commit(np.ones(1), np.zeros(1), np.zeros(1), np.zeros(1), np.array([1.0]), np.zeros(1), np.zeros(1))
     g.set_time(0.0)
     g.evolve(0.25)
     st = g.get_state()
     assert st[1][0] == pytest.approx(0.25, rel=1e-15) and st[4][0] == 1.0
+
+
+def test_fp64_microbenchmarks(ctx):
+    """The roofline denominators: the DFMA-only peak, and the same chains with one independent MUFU.RSQ64H per 32
+    DFMAs (the force kernel's ratio) -- the 64-bit rsqrt takes no FP64 issue slots."""
+    peak, mixed = ctx.fp64_peak_tflops(), ctx.fp64_with_rsqrt_tflops()
+    assert 20.0 < peak < 45.0
+    assert 0.95 < mixed / peak < 1.03
 
 
 def test_full_size_properties_1e5(pkg, grav):
