@@ -73,6 +73,7 @@ SIGNATURES = {
     "al26_set_decomposition": (C.c_int, [_VP, C.c_int, C.c_double]),
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
     "al26_grav_engine_steps": (C.c_int, [_VP, _PI64, C.POINTER(C.c_int)]),
+    "al26_dbg_engine_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "al26_set_fuse_max": (C.c_int, [_VP, C.c_int]),
     "al26_grav_fused_steps": (C.c_int, [_VP, _PI64]),
     "al26_grav_fuse_profile": (C.c_int, [_VP, _PI64]),
@@ -257,6 +258,15 @@ def decomposition(n_act, n_tot, sm_count=148, variant=0, big_nact=2048):
     if rc != 0:
         raise Al26Error(rc, "bad arguments")
     return dict(zip(("ipt", "ti", "n_itiles", "n_jsplit", "jchunk", "slot_stride", "part_capacity", "grid"), list(out)))
+
+
+def engine_plan(n, max_smem_per_block=232448):
+    """host-only: (cluster size or 0, particles per CTA, shared-memory bytes per CTA) of the cluster engine for n particles"""
+    cs, p, b = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = load().al26_dbg_engine_plan(int(n), int(max_smem_per_block), C.byref(cs), C.byref(p), C.byref(b))
+    if rc != 0:
+        raise Al26Error(rc, "bad arguments")
+    return cs.value, p.value, b.value
 
 
 def dist_unique_id():

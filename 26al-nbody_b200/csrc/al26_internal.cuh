@@ -131,6 +131,7 @@ struct GravDev {
 constexpr int ENG_MAX_ACT = 32;  // largest block the engine steps itself
 constexpr int ENG_CS_MAX = 16;   // cluster size: 8 (portable) or 16
 int engine_smem_bytes(int p_cap);
+bool engine_plan(int n, int max_smem, int *cs_out, int *p_cap_out);
 cudaError_t engine_kernel_setup(int max_smem_optin);
 bool engine_fits(int cs, int p_cap, int max_smem_optin);
 

@@ -310,16 +310,12 @@ int reduce_tnext(al26_ctx *c, int phase) {
 void decide_engine(al26_ctx *c) {
   c->engine_on = false;
   if ((c->step_mode != 2 && c->step_mode != -1) || c->world != 1 || !c->engine_ok || !c->committed) return;
-  const int n = c->g.n_tot;
-  for (int cs = 8; cs <= ENG_CS_MAX; cs *= 2) {
-    const int p_cap = (((n + cs - 1) / cs) + 7) & ~7;
-    if (engine_fits(cs, p_cap, c->max_smem_optin)) {
-      c->engine_on = true;
-      c->engine_cs = cs;
-      c->engine_p = p_cap;
-      return;
-    }
-  }
+  int cs = 0, p_cap = 0;
+  if (!engine_plan(c->g.n_tot, c->max_smem_optin, &cs, &p_cap)) return;
+  if (!engine_fits(cs, p_cap, c->max_smem_optin)) return;  // the driver's say on co-residency of the cluster
+  c->engine_on = true;
+  c->engine_cs = cs;
+  c->engine_p = p_cap;
 }
 
 // one block step (or the init / sync variant) enqueued on the stream
@@ -1239,6 +1235,19 @@ int al26_dbg_decomposition(int n_act, int n_tot, int sm_count, int variant, int 
   const Decomp d = make_decomp(n_act, n_tot, tab.data(), ipt, big_nact);
   out8[0] = d.ipt; out8[1] = d.ti; out8[2] = d.n_itiles; out8[3] = d.n_jsplit; out8[4] = d.jchunk;
   out8[5] = d.slot_stride; out8[6] = part_capacity(n_tot, grid); out8[7] = grid;
+  return 0;
+}
+
+int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *particles_per_cta, int *smem_bytes) {
+  if (!cluster_size || !particles_per_cta || !smem_bytes || n < 1 || max_smem_per_block < 0) return AL26_EINVAL;
+  int cs = 0, p_cap = 0;
+  if (!engine_plan(n, max_smem_per_block, &cs, &p_cap)) {
+    *cluster_size = *particles_per_cta = *smem_bytes = 0;
+    return 0;
+  }
+  *cluster_size = cs;
+  *particles_per_cta = p_cap;
+  *smem_bytes = engine_smem_bytes(p_cap);
   return 0;
 }
 

@@ -55,6 +55,21 @@ constexpr int ENG_BYTES_PER_PARTICLE = 6 * 32 + 2 * 8;  // pos, vel, acc, jrk, p
 
 int engine_smem_bytes(int p_cap) { return (int)sizeof(EngShared) + p_cap * ENG_BYTES_PER_PARTICLE; }
 
+// The smallest cluster (8, then 16 CTAs) whose CTAs can hold n / cluster particles each within `max_smem` bytes of
+// shared memory per block.  Pure arithmetic (host; also behind the host-only diagnostic al26_dbg_engine_plan).
+bool engine_plan(int n, int max_smem, int *cs_out, int *p_cap_out) {
+  if (n < 1) return false;
+  for (int cs = 8; cs <= ENG_CS_MAX; cs *= 2) {
+    const int p_cap = (((n + cs - 1) / cs) + 7) & ~7;
+    if (engine_smem_bytes(p_cap) <= max_smem) {
+      *cs_out = cs;
+      *p_cap_out = p_cap;
+      return true;
+    }
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(ENG_T, 1) k_engine(const GravDev g, const int phase, const int p_cap) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();

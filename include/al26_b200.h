@@ -153,7 +153,7 @@ int al26_set_big_block(al26_ctx *ctx, int n_act_min);
  * applies at the next al26_grav_commit */
 int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_pairs);
 /* tuning hook: how block steps are driven on one GPU.  -1 (default): automatic -- 2 when the particles fit one
- * cluster (N <= ~14000), else 0.  0: a CUDA graph of three kernels per block
+ * cluster (N <= ~13000), else 0.  0: a CUDA graph of three kernels per block
  * step, relaunched until the device reports the call done; 1: one persistent cooperative kernel runs the
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).
  * Bit-identical results (except the loop kernel's fused small steps, al26_set_fuse_max: identical integer work,
@@ -165,11 +165,15 @@ int al26_set_step_mode(al26_ctx *ctx, int mode);
  * steps (<= 32 active particles) on chip -- DSMEM hops and hardware cluster barriers (~0.1-0.2 us) instead of L2
  * round trips, atomics and fences (~0.4 us each) -- writing corrected particles through to the global records; a
  * bigger block is left to the grid-wide kernels that follow in the graph.  Applies when the particles fit one
- * cluster (N <= ~14000 on B200; otherwise the mode behaves like 0).  Identical integer work, positions to rounding;
+ * cluster (N <= ~13000 on B200; otherwise the mode behaves like 0).  Identical integer work, positions to rounding;
  * measured 1.15-1.4x faster per block step than mode 0 at N = 1e3..1e4.
  * diagnostic: block steps the engine took since the last commit, and its cluster size (0 = engine not in use;
  * cluster_size may be NULL) */
 int al26_grav_engine_steps(al26_ctx *ctx, int64_t *n_engine, int *cluster_size);
+/* host-only diagnostic (needs no GPU): the cluster the engine would use for n particles when a block may opt in to
+ * max_smem_per_block bytes of shared memory (232448 on B200) -- cluster size (8 or 16; 0 = the particles do not fit),
+ * particles per CTA, shared memory per CTA */
+int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *particles_per_cta, int *smem_bytes);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
  * else off) take the fused small-step path

@@ -160,3 +160,26 @@ def test_force_work_decomposition_invariants(pkg):
                     assert n_act >= 2048
     with pytest.raises(lib.Al26Error):
         lib.decomposition(5, 3)
+
+
+def test_cluster_engine_plan(pkg):
+    """host-side check of the cluster engine's capacity plan (hermite_engine.cu: engine_plan): the smallest cluster
+    whose CTAs hold their share of the particles in shared memory; 8 CTAs while that fits, 16 up to ~1.3e4 particles."""
+    lib = importlib.import_module("26al-nbody_b200._lib")
+    last_cs = 8
+    for n in (1, 2, 7, 8, 9, 1000, 3000, 6000, 6592, 6593, 7000, 10_000, 13_000, 13_184, 13_185, 14_000, 20_000, 100_000):
+        cs, p, b = lib.engine_plan(n)
+        if cs == 0:
+            assert (p, b) == (0, 0) and n > 13_184
+            last_cs = 99
+            continue
+        assert cs in (8, 16) and cs >= last_cs            # monotone in n
+        last_cs = cs
+        assert p % 8 == 0 and cs * p >= n > cs * (p - 8) - cs  # every particle has a home, no CTA over-sized
+        assert b <= 232448 and b == lib.engine_plan(cs * p)[2]
+        if cs == 16:  # 8 CTAs really were too few
+            assert n > 6592
+    assert lib.engine_plan(10_000)[0] == 16 and lib.engine_plan(1000)[0] == 8   # BASELINE configs 2 and 1
+    assert lib.engine_plan(10_000, 100_000)[0] == 0      # a device with less shared memory: no engine
+    with pytest.raises(lib.Al26Error):
+        lib.engine_plan(0)
