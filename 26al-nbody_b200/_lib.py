@@ -47,6 +47,7 @@ SIGNATURES = {
     "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
     "al26_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
     "al26_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
+    "al26_grav_set_reinit_policy": (C.c_int, [_VP, C.c_int]),
     "al26_grav_set_time": (C.c_int, [_VP, C.c_double]),
     "al26_grav_get_time": (C.c_int, [_VP, _PD]),
     "al26_grav_evolve": (C.c_int, [_VP, C.c_double, _PI64, _PI64]),

@@ -106,6 +106,7 @@ struct GravDev {
   int big_nact;           // blocks of at least this many particles use force_ipt i-particles per lane
   double eps2, eta, dt_max, dt_min;
   double Dmax;  // largest step of the current call's dyadic ladder (= hdr->D; set by the host at begin_evolve)
+  int keep_dt;  // MODE_INIT only: recompute acc / jerk / pot, leave every particle's timestep alone (mass-only update)
   double4 *pos, *vel, *acc, *jrk;
   double *t, *dt;
   double4 *jpos, *jvel;

@@ -87,7 +87,11 @@ struct al26_ctx {
 
   // gravity
   GravDev g{};
-  bool committed = false, dirty = true, in_evolve = false;
+  bool committed = false, in_evolve = false;
+  // 0 = forces and timesteps valid; 1 = masses changed (forces stale, timesteps still those of the last
+  // synchronisation); 2 = nothing valid yet (after commit / set_params)
+  int dirty = 2;
+  int reinit_policy = 0;  // what a mass-only update costs: 0 = forces only, timesteps kept; 1 = forces + initial timesteps
   double t_model = 0.0, t_end_pending = 0.0;
   double eps2 = 0.0, eta = 0.14, dt_max = 0.125, dt_min = 9.094947017729282e-13 /* 2^-40 */;
   int64_t n_tot = 0;
@@ -382,6 +386,9 @@ int reset_ctrl(al26_ctx *c, int zero_counters) {
 int dist_single(al26_ctx *c, int mode);
 int initialise_forces(al26_ctx *c) {
   int rc;
+  // mass-only update (al26_grav_set_mass between two evolve calls): every particle sits at the synchronisation time
+  // with the timestep the synchronisation step gave it; under policy 0 only acc / jerk / pot are recomputed
+  c->g.keep_dt = (c->dirty == 1 && c->reinit_policy == 0) ? 1 : 0;
   if (is_p2p(c)) {
     rc = dist_single(c, MODE_INIT);
   } else {
@@ -389,7 +396,7 @@ int initialise_forces(al26_ctx *c) {
     rc = enqueue_step(c, MODE_INIT, 0);
   }
   if (rc) return rc;
-  c->dirty = false;
+  c->dirty = 0;
   return 0;
 }
 
@@ -669,8 +676,16 @@ int al26_grav_set_params(al26_ctx *c, double eps2, double eta, double dt_max, do
   c->eta = eta;
   c->dt_max = pow2floor_h(dt_max);
   c->dt_min = pow2floor_h(dt_min);
-  c->dirty = true;
+  c->dirty = 2;
   c->graph_stale = c->committed;
+  return 0;
+}
+
+int al26_grav_set_reinit_policy(al26_ctx *c, int policy) {
+  if (!c) return AL26_EINVAL;
+  if (policy != 0 && policy != 1) return fail(c, AL26_EINVAL, "re-initialisation policy must be 0 (keep timesteps) or 1 (initial timesteps)");
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_reinit_policy during evolve");
+  c->reinit_policy = policy;
   return 0;
 }
 
@@ -768,7 +783,7 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   CU(cudaStreamSynchronize(c->stream));
   c->n_tot = n;
   c->committed = true;
-  c->dirty = true;
+  c->dirty = 2;
   rc = build_graph(c);
   if (rc) {
     free_gravity(c);
@@ -788,7 +803,7 @@ int al26_grav_set_mass(al26_ctx *c, int64_t n, const double *m) {
   k_set_mass<<<nblk(nl), 256, 0, c->stream>>>((int)nl, c->scratch, c->g.pos);
   c->launches++;
   CU(cudaStreamSynchronize(c->stream));  // the host buffer may be reused by the caller
-  c->dirty = true;
+  if (c->dirty < 1) c->dirty = 1;
   return 0;
 }
 
@@ -818,24 +833,18 @@ int al26_grav_initialize(al26_ctx *c) {
   return 0;
 }
 
-int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t *n_pairs) {
-  if (!c) return AL26_EINVAL;
-  if (n_block_steps) *n_block_steps = 0;
-  if (n_pairs) *n_pairs = 0;
-  if (c->committed && !c->in_evolve && t_end == c->t_model) return 0;
-  CU(cudaSetDevice(c->device));
-  const int64_t l0 = c->launches;
-  CU(cudaEventRecord(c->ev0, c->stream));
-  int rc = begin_evolve(c, t_end);
-  if (rc) return rc;
+// the part of al26_grav_evolve between begin_evolve and the end of the call: any failure in here leaves through the
+// caller, which clears in_evolve (so a CUDA error does not wedge the context in "evolve already in progress")
+static int evolve_run(al26_ctx *c, const int64_t l0, int64_t *n_block_steps, int64_t *n_pairs) {
+  int rc;
   if (is_p2p(c)) {
     while (true) {
-      if ((rc = run_dist(c, MODE_STEP, 1 << 30))) { c->in_evolve = false; return rc; }
+      if ((rc = run_dist(c, MODE_STEP, 1 << 30))) return rc;
       if (c->h_hdr->done) break;
     }
   } else if (use_loop(c)) {
     while (true) {
-      if ((rc = run_loop(c, 1 << 30))) { c->in_evolve = false; return rc; }
+      if ((rc = run_loop(c, 1 << 30))) return rc;
       if (c->h_hdr->done) break;
     }
   } else {
@@ -848,13 +857,12 @@ int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t 
         launches_needed++;
       }
       batch = 1;
-      if ((rc = read_header(c))) { c->in_evolve = false; return rc; }
+      if ((rc = read_header(c))) return rc;
       if (c->h_hdr->done) break;
     }
     c->expected_graph_launches = launches_needed;
   }
-  rc = finish_evolve(c);
-  if (rc) { c->in_evolve = false; return rc; }
+  if ((rc = finish_evolve(c))) return rc;
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaEventSynchronize(c->ev1));
   float ms = 0.f;
@@ -864,6 +872,21 @@ int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t 
   if (n_block_steps) *n_block_steps = c->h_hdr->n_steps;
   if (n_pairs) *n_pairs = c->h_hdr->n_pairs;
   return 0;
+}
+
+int al26_grav_evolve(al26_ctx *c, double t_end, int64_t *n_block_steps, int64_t *n_pairs) {
+  if (!c) return AL26_EINVAL;
+  if (n_block_steps) *n_block_steps = 0;
+  if (n_pairs) *n_pairs = 0;
+  if (c->committed && !c->in_evolve && t_end == c->t_model) return 0;
+  CU(cudaSetDevice(c->device));
+  const int64_t l0 = c->launches;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  int rc = begin_evolve(c, t_end);
+  if (rc) return rc;
+  rc = evolve_run(c, l0, n_block_steps, n_pairs);
+  if (rc) c->in_evolve = false;  // every error exit: the context stays usable (the particle state is undefined after a CUDA error)
+  return rc;
 }
 
 int al26_grav_dbg_begin(al26_ctx *c, double t_end) {
@@ -949,7 +972,9 @@ int al26_grav_dbg_finish(al26_ctx *c) {
   if (!c) return AL26_EINVAL;
   if (!c->in_evolve) return fail(c, AL26_ESTATE, "dbg_finish outside begin");
   CU(cudaSetDevice(c->device));
-  return finish_evolve(c);
+  const int rc = finish_evolve(c);
+  if (rc) c->in_evolve = false;
+  return rc;
 }
 
 int al26_grav_get_state(al26_ctx *c, int64_t n, double *m, double *x, double *y, double *z, double *vx, double *vy,

@@ -298,15 +298,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, c
     FT_STAMP(fa0);
     if (fuse) phase_scan_chunk<false>(g, cur, nxt, tn, CHUNK_J0, CHUNK_CNT, &sm.pos[0][0], &sm.vel[0][0], sh);
     else phase_predict_list<MODE_STEP, false>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh);
+    PROF(0)
+    FT_STAMP(fa1);
+    if (!grid_barrier(g.hdr, target, n_ctas)) break;
+    // Recycle the record of the step before last only now: the previous step's fused path ends with every CTA polling
+    // old->pad[1] with no barrier behind it, so a reset before this barrier could be seen by a CTA that is still
+    // polling.  Past the barrier every CTA has left those polls, and the reset is ordered before the record's next
+    // use (as `nxt` of the following step) by this step's later barriers / release counters, all of which CTA 0 takes
+    // part in after these stores.
     if (first) {
       old->t_next_bits = INF_BITS;
       old->n_act = 0;
       old->work_counter = 0;
       old->pad[1] = 0;
     }
-    PROF(0)
-    FT_STAMP(fa1);
-    if (!grid_barrier(g.hdr, target, n_ctas)) break;
     PROF(1)
     const int n_act = __ldcg(&cur->n_act);
     FT_STAMP(fa2);
@@ -454,14 +459,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     }
     if (fuse) phase_scan_chunk<true>(g, cur, nxt, tn, CHUNK_J0, CHUNK_CNT, &sm.pos[0][0], &sm.vel[0][0], sh, prev_exch ? xid : 0ull);
     else phase_predict_list<MODE, true>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh, prev_exch ? xid : 0ull);
-    if (first) {
+    if (!grid_barrier(g.hdr, target, n_ctas)) break;
+    if (first) {  // after the barrier: nobody polls the previous step's counters any more (see k_loop)
       old->t_next_bits = INF_BITS;
       old->n_act = 0;
       old->work_counter = 0;
       old->pad[0] = 0;
       old->pad[1] = 0;
     }
-    if (!grid_barrier(g.hdr, target, n_ctas)) break;
     const int n_all = __ldcg(&cur->n_act);
     const int n_own = __ldcg(&cur->pad[0]);
     const bool exchange = (MODE != MODE_STEP) || n_all >= g.split_min;

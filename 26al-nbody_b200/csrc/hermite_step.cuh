@@ -232,6 +232,13 @@ struct NewState {
   double t, dt;
 };
 
+// With softening the force kernel's masked rsqrt does not drop the self pair (r^2 + eps2 = eps2 > 0): dx = 0 nulls its
+// acceleration and jerk, but -m_i/eps lands in the potential.  Taken out again here, so `pot` is the potential of the
+// OTHER particles, as in every direct N-body code (and the oracle).
+__device__ __forceinline__ double pot_without_self(const double pot, const double m_i, const double eps2) {
+  return (eps2 > 0.0) ? pot + m_i * (1.0 / sqrt(eps2)) : pot;
+}
+
 // where a corrected particle goes: the local state, or (peer-memory mode) every rank's staging slab
 template <bool DIST>
 __device__ __forceinline__ void store_state(const GravDev &g, const int i, const NewState &n, const unsigned long long step_id) {
@@ -266,7 +273,7 @@ __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, 
   const double a1[3] = {r[0], r[1], r[2]};
   const double j1[3] = {r[3], r[4], r[5]};
   NewState n;
-  n.acc = make_double4(a1[0], a1[1], a1[2], r[6]);
+  n.acc = make_double4(a1[0], a1[1], a1[2], pot_without_self(r[6], in.xp.w, g.eps2));
   n.jrk = make_double4(j1[0], j1[1], j1[2], 0.0);
   const double4 a0v = in.a0, j0v = in.j0;
   const double4 xpv = in.xp, vpv = in.vp;
@@ -328,7 +335,7 @@ template <int MODE, bool DIST>
 __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, const int slot, const double r[7],
                                            unsigned long long &c_bits, const unsigned long long step_id) {
   if (MODE == MODE_RAW) {
-    g.raw_a[slot] = make_double4(r[0], r[1], r[2], r[6]);
+    g.raw_a[slot] = make_double4(r[0], r[1], r[2], pot_without_self(r[6], g.jpos[g.i0 + g.list[slot]].w, g.eps2));
     g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
     return;
   }
@@ -337,7 +344,7 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, co
     const double a1[3] = {r[0], r[1], r[2]};
     const double j1[3] = {r[3], r[4], r[5]};
     NewState n;
-    n.acc = make_double4(a1[0], a1[1], a1[2], r[6]);
+    n.acc = make_double4(a1[0], a1[1], a1[2], pot_without_self(r[6], g.jpos[g.i0 + i].w, g.eps2));
     n.jrk = make_double4(j1[0], j1[1], j1[2], 0.0);
     const double sa = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
     const double sj = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
@@ -347,7 +354,7 @@ __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, co
     if (dt0 > g.dt_max) dt0 = g.dt_max;
     double dd = pow2floor(dt0);
     if (dd < g.dt_min) dd = g.dt_min;
-    n.dt = dd;
+    n.dt = g.keep_dt ? g.dt[i] : dd;
     n.t = 0.0;
     if (!DIST) {  // positions and velocities are untouched
       g.acc[i] = n.acc; g.jrk[i] = n.jrk; g.dt[i] = n.dt; g.t[i] = n.t;

@@ -49,6 +49,10 @@ class GravityCore:
     def set_mass(self, m):
         self.ctx.chk(self.L.al26_grav_set_mass(self.h, len(m), _lib.f64(m)))
 
+    def set_reinit_policy(self, policy):
+        """mass-only update: 0 = recompute forces, keep timesteps (default, ph4's recommit); 1 = forces + initial timesteps"""
+        self.ctx.chk(self.L.al26_grav_set_reinit_policy(self.h, int(policy)))
+
     def set_time(self, t):
         self.ctx.chk(self.L.al26_grav_set_time(self.h, float(t)))
 

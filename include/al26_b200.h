@@ -87,6 +87,14 @@ int al26_grav_commit(al26_ctx *ctx, int64_t n, const double *m, const double *x,
 /* replaces: `stel_to_grav.copy_attributes(["mass"])` (al26_nbody.py:871,874): legal between
  * evolve calls; forces and timesteps are re-initialised at the next evolve. */
 int al26_grav_set_mass(al26_ctx *ctx, int64_t n, const double *m);
+/* what such a mass-only update costs at the next evolve (every particle is synchronised at model time then):
+ * 0 (default): acc / jerk / pot are recomputed with the new masses, every particle keeps the timestep the
+ *    synchronisation step gave it -- ph4's recommit_particles ("recompute forces ... we don't recompute the time
+ *    steps" [upstream amuse_ph4 interface.cc, from memory]) behind the AMUSE state machine that the script's
+ *    per-step mass channel triggers (al26_nbody.py:871,874);
+ * 1: forces AND initial timesteps eta/16 |a|/|jerk| again, as after a commit (the round-1 behaviour; costs the
+ *    block steps every particle then needs to climb back up the ladder). */
+int al26_grav_set_reinit_policy(al26_ctx *ctx, int policy);
 /* replaces: `gravity.model_time` setter / getter (al26_nbody.py:763,1101,1736). */
 int al26_grav_set_time(al26_ctx *ctx, double t);
 int al26_grav_get_time(al26_ctx *ctx, double *t);

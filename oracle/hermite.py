@@ -14,7 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhermite_oracle.so")
+_SO_NATIVE = os.path.join(_HERE, "libhermite_oracle_native.so")
 _lib = None
+_flavour = "x86-64-v3"
 
 _D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _I32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -25,6 +27,26 @@ def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
+
+
+def prefer_native():
+    """bench.py's CPU legs: build the oracle with -march=native ON THE BOX THAT RUNS IT (the portable
+    x86-64-v3 build travels with the snapshot; a native build made elsewhere could SIGILL) and use it.
+    Must be called before the first oracle call; falls back to the portable build if gcc fails."""
+    global _SO, _flavour
+    if _lib is not None:
+        return _flavour
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if os.path.exists(_SO_NATIVE):
+            _SO, _flavour = _SO_NATIVE, "native"
+    except Exception:
+        pass
+    return _flavour
+
+
+def flavour():
+    return _flavour
 
 
 def lib():
@@ -38,6 +60,7 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_params.argtypes = [C.c_void_p] + [C.c_double] * 4
         L.orc_set_long_double.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_reinit_policy.argtypes = [C.c_void_p, C.c_int]
         L.orc_commit.argtypes = [C.c_void_p, C.c_int64] + [_D] * 7
         L.orc_set_mass.argtypes = [C.c_void_p, C.c_int64, _D]
         L.orc_set_time.argtypes = [C.c_void_p, C.c_double]
@@ -109,6 +132,10 @@ class HermiteOracle:
 
     def set_mass(self, m):
         self._chk(self.L.orc_set_mass(self.h, self.n, _c(m)))
+
+    def set_reinit_policy(self, policy):
+        """mass-only update: 0 = recompute forces, keep timesteps (default); 1 = forces + initial timesteps"""
+        self._chk(self.L.orc_set_reinit_policy(self.h, int(policy)))
 
     def set_time(self, t):
         self.L.orc_set_time(self.h, float(t))

@@ -23,10 +23,15 @@
  * THE SCHEME (shared spec with the CUDA path; all in N-body units, G = 1):
  *   state per particle: m, x, v, a, jerk, pot, t (relative to the start of the
  *   current evolve call, "tau"), dt (power of two).
- *   init (first evolve after commit / set_mass, "dirty"):
+ *   init (first evolve after commit / set_params):
  *       a, jerk, pot on all particles from current x, v;
  *       dt0 = eta * 0.0625 * |a|/|jerk|  (dt_max if |a| or |jerk| == 0),
  *       dt  = max(dt_min, pow2floor(min(dt0, 2^-5, dt_max)))
+ *   mass-only update (set_mass between two evolve calls; the script does this every outer step,
+ *       al26_nbody.py:874): a, jerk, pot recomputed from the synchronised x, v with the new masses;
+ *       every dt_i keeps the value the synchronisation step gave it (reinit_policy 0, the default --
+ *       ph4's recommit_particles "recompute forces ... we don't recompute the time steps"
+ *       [upstream, from memory]); reinit_policy 1 re-derives the initial timesteps as above.
  *   begin(t_end): span = t_end - t_model; D = min(dt_max, pow2floor(span));
  *       dt_i = min(dt_i, D); tau_i = 0
  *   block step: tau_next = min_i(tau_i + dt_i); stop if tau_next > span;
@@ -65,7 +70,8 @@ typedef struct {
   int64_t n;
   double eps2, eta, dt_max, dt_min;
   double t_model;
-  int dirty;      /* forces / timesteps need (re)initialisation */
+  int dirty;      /* 0 = forces and timesteps valid; 1 = masses changed since the last synchronisation; 2 = nothing valid */
+  int reinit_policy; /* mass-only update: 0 = recompute forces, keep timesteps; 1 = forces + initial timesteps */
   int in_evolve;  /* between begin and finish */
   double span, D;
   int use_long_double;
@@ -88,7 +94,7 @@ orc_t *orc_create(int64_t n) {
   o->eta = 0.14;
   o->dt_max = 0.125;
   o->dt_min = ldexp(1.0, -40);
-  o->dirty = 1;
+  o->dirty = 2;
   double **arrs[] = {&o->m, &o->x, &o->y, &o->z, &o->vx, &o->vy, &o->vz, &o->ax, &o->ay, &o->az,
                      &o->jx, &o->jy, &o->jz, &o->pot, &o->t, &o->dt, &o->px, &o->py, &o->pz,
                      &o->pvx, &o->pvy, &o->pvz, &o->nax, &o->nay, &o->naz, &o->njx, &o->njy,
@@ -119,7 +125,12 @@ int orc_set_params(orc_t *o, double eps2, double eta, double dt_max, double dt_m
   o->dt_max = ldexp(1.0, e - 1);
   frexp(dt_min, &e);
   o->dt_min = ldexp(1.0, e - 1);
-  o->dirty = 1;
+  o->dirty = 2;
+  return 0;
+}
+int orc_set_reinit_policy(orc_t *o, int policy) {
+  if (policy != 0 && policy != 1) return -1;
+  o->reinit_policy = policy;
   return 0;
 }
 void orc_set_long_double(orc_t *o, int on) { o->use_long_double = on; }
@@ -130,13 +141,13 @@ int orc_commit(orc_t *o, int64_t n, const double *m, const double *x, const doub
   size_t b = (size_t)n * sizeof(double);
   memcpy(o->m, m, b); memcpy(o->x, x, b); memcpy(o->y, y, b); memcpy(o->z, z, b);
   memcpy(o->vx, vx, b); memcpy(o->vy, vy, b); memcpy(o->vz, vz, b);
-  o->dirty = 1;
+  o->dirty = 2;
   return 0;
 }
 int orc_set_mass(orc_t *o, int64_t n, const double *m) {
   if (n != o->n) return -1;
   memcpy(o->m, m, (size_t)n * sizeof(double));
-  o->dirty = 1;
+  if (o->dirty < 1) o->dirty = 1;
   return 0;
 }
 int orc_set_time(orc_t *o, double t) { o->t_model = t; return 0; }
@@ -161,7 +172,7 @@ static void force_double(const orc_t *o, int64_t n_act, const int32_t *idx) {
       const double dvx = pvx[j] - vxi, dvy = pvy[j] - vyi, dvz = pvz[j] - vzi;
       const double r2 = dx * dx + dy * dy + dz * dz + eps2;
       const double rv = dx * dvx + dy * dvy + dz * dvz;
-      const double rinv = (r2 > 0.0) ? 1.0 / sqrt(r2) : 0.0;
+      const double rinv = (r2 > 0.0 && j != i) ? 1.0 / sqrt(r2) : 0.0; /* self pair: out, also when softened */
       const double rinv2 = rinv * rinv;
       const double mrinv = m[j] * rinv;
       const double mrinv3 = mrinv * rinv2;
@@ -191,7 +202,7 @@ static void force_long_double(const orc_t *o, int64_t n_act, const int32_t *idx)
       const long double dx = o->px[j] - xi, dy = o->py[j] - yi, dz = o->pz[j] - zi;
       const long double dvx = o->pvx[j] - vxi, dvy = o->pvy[j] - vyi, dvz = o->pvz[j] - vzi;
       const long double r2 = dx * dx + dy * dy + dz * dz + eps2;
-      if (!(r2 > 0.0L)) continue;
+      if (!(r2 > 0.0L) || j == i) continue;
       const long double rv = dx * dvx + dy * dvy + dz * dvz;
       const long double rinv = 1.0L / sqrtl(r2);
       const long double rinv2 = rinv * rinv;
@@ -304,10 +315,12 @@ NOFMA static void initialise(orc_t *o) {
   predict_all(o, 0.0); /* s = 0: predicted == current */
   force(o, n, o->active);
   const double lim = ldexp(1.0, -5);
+  const int keep_dt = (o->dirty == 1 && o->reinit_policy == 0);
   for (int64_t i = 0; i < n; i++) {
     o->ax[i] = o->nax[i]; o->ay[i] = o->nay[i]; o->az[i] = o->naz[i];
     o->jx[i] = o->njx[i]; o->jy[i] = o->njy[i]; o->jz[i] = o->njz[i];
     o->pot[i] = o->npot[i];
+    if (keep_dt) continue; /* mass-only update: the timestep of the last synchronisation step stands */
     const double sa = o->ax[i] * o->ax[i] + o->ay[i] * o->ay[i] + o->az[i] * o->az[i];
     const double sj = o->jx[i] * o->jx[i] + o->jy[i] * o->jy[i] + o->jz[i] * o->jz[i];
     double dt0 = o->dt_max;

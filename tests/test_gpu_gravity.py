@@ -128,6 +128,102 @@ def test_initialize_and_stepwise_parity(pkg, grav, n, model):
     assert grav.get_time() == t_end
 
 
+@pytest.mark.parametrize("n,model", [(100_000, "plummer"), (10_000, "fractal")])
+def test_stepwise_parity_at_baseline_sizes(pkg, grav, n, model):
+    """BASELINE configs 3 (N = 1e5 Plummer) and 2 (N = 1e4 fractal D = 1.6, eps = 0) against the ORACLE, block step by
+    block step: active sets and the dyadic ladder bit-exact, acc / jerk <= 1e-12, >= 60 block steps, then the rest of
+    the call and the synchronisation step."""
+    p = make(pkg, n, seed=n + 7, model=model)
+    o = H.HermiteOracle(n)
+    o.commit(*p)
+    grav.commit(*p)
+    o.initialize(); grav.initialize()
+    ga, oa = grav.get_acc_jerk(), o.get_acc_jerk()
+    assert vec_rel(ga[:3], oa[:3]) < TOL and vec_rel(ga[3:6], oa[3:6]) < TOL
+    assert np.max(np.abs(ga[6] - oa[6]) / np.abs(oa[6])) < TOL
+    assert np.array_equal(grav.get_timesteps()[1], o.get_timesteps()[1])
+    t_end = 2.0 ** -10
+    o.begin(t_end); grav.begin(t_end)
+    compared = 0
+    for step in range(64):
+        oi, ot = o.get_active()
+        nd_o, fin_o = o.advance(1)
+        nd_g, fin_g = grav.advance(1)
+        assert fin_o == fin_g and nd_o == nd_g
+        if fin_o:
+            break
+        assert np.array_equal(grav.get_last_active(), oi), f"active set differs at block step {step}"
+        gt_, gdt = grav.get_timesteps(); ot_, odt = o.get_timesteps()
+        assert np.array_equal(gt_, ot_) and np.array_equal(gdt, odt), f"ladder differs at block step {step}"
+        compared += 1
+    assert compared >= 60
+    ga, oa = grav.get_acc_jerk(), o.get_acc_jerk()  # the forces the last correctors stored
+    assert vec_rel(ga[:3], oa[:3]) < TOL and vec_rel(ga[3:6], oa[3:6]) < TOL
+    o.advance(-1); grav.advance(-1)
+    o.finish(); grav.finish()
+    assert o.counters()[0] >= 61
+    gs, os_ = grav.get_state(), o.get_state()
+    assert vec_rel(gs[1:4], os_[1:4]) < 1e-10 and vec_rel(gs[4:7], os_[4:7]) < 1e-10
+    assert np.array_equal(grav.get_timesteps()[1], o.get_timesteps()[1])  # timesteps after the synchronisation step
+    assert grav.get_time() == t_end
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_mass_update_policies_match_the_oracle(pkg, grav, policy):
+    """al26_nbody.py:874 feeds new masses in after every outer step.  Policy 0 (default): forces recomputed, timesteps
+    of the synchronisation step kept; policy 1: initial timesteps again.  Both against the oracle, integer work exact."""
+    n = 700
+    p = make(pkg, n, seed=21)
+    o = H.HermiteOracle(n); o.commit(*p); o.set_reinit_policy(policy)
+    grav.commit(*p); grav.set_reinit_policy(policy)
+    try:
+        assert grav.evolve(0.01) == o.evolve(0.01)
+        dt_sync = grav.get_timesteps()[1].copy()
+        assert np.array_equal(dt_sync, o.get_timesteps()[1])
+        a_old = np.stack(grav.get_acc_jerk()[:3])
+        m2 = p[0] * np.random.default_rng(2).uniform(0.9, 1.0, n)
+        grav.set_mass(m2); o.set_mass(m2)
+        grav.initialize(); o.initialize()
+        ga, oa = grav.get_acc_jerk(), o.get_acc_jerk()
+        assert vec_rel(ga[:3], oa[:3]) < TOL and vec_rel(ga[3:6], oa[3:6]) < TOL
+        assert not np.array_equal(np.stack(ga[:3]), a_old)  # the forces did see the new masses
+        dt_now = grav.get_timesteps()[1]
+        assert np.array_equal(dt_now, o.get_timesteps()[1])
+        if policy == 0:
+            assert np.array_equal(dt_now, dt_sync)
+        else:
+            assert np.all(dt_now <= 2.0 ** -5) and not np.array_equal(dt_now, dt_sync)
+        w_g, w_o = grav.evolve(0.02), o.evolve(0.02)
+        assert w_g == w_o
+        gs, os_ = grav.get_state(), o.get_state()
+        assert np.array_equal(gs[0], m2) and vec_rel(gs[1:4], os_[1:4]) < 1e-9
+    finally:
+        grav.set_reinit_policy(0)
+
+
+def test_softened_potential_excludes_the_self_pair(pkg, grav):
+    """eps2 > 0: the masked rsqrt lets the self pair through (r^2 + eps2 > 0); its -m_i/eps is taken out of pot again"""
+    rng = np.random.default_rng(4)
+    n, eps2 = 5, 0.25
+    m = rng.uniform(0.5, 1.5, n)
+    x, y, z = rng.normal(size=(3, n))
+    v = rng.normal(size=(3, n))
+    pot = grav.force(m, x, y, z, *v, eps2=eps2)[6]
+    want = np.array([-sum(m[j] / np.sqrt((x[i] - x[j]) ** 2 + (y[i] - y[j]) ** 2 + (z[i] - z[j]) ** 2 + eps2)
+                          for j in range(n) if j != i) for i in range(n)])
+    assert np.max(np.abs(pot - want) / np.abs(want)) < 1e-14
+    g2 = grav
+    g2.set_params(eps2=eps2)
+    try:
+        g2.commit(m, x, y, z, *v)
+        g2.initialize()
+        assert np.max(np.abs(g2.get_acc_jerk()[6] - want) / np.abs(want)) < 1e-14
+        k, u, _ = g2.energies()
+        assert u == pytest.approx(0.5 * np.sum(m * want), rel=1e-13)
+    finally:
+        g2.set_params()
+
+
 def test_evolve_matches_oracle_counts_and_energy(pkg, grav):
     n = 1000
     p = make(pkg, n, seed=3)

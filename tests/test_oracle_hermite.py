@@ -172,3 +172,32 @@ def test_figure_eight_three_body_returns_after_one_period():
         assert np.max(np.abs(a - b)) < 5e-5                # back at the start after one period
     k1, u1, _ = o.energies()
     assert abs((k1 + u1) - (k0 + u0)) / abs(k0 + u0) < 1e-8
+
+
+def test_mass_update_policy_and_softened_self_pair():
+    """Mass-only update: policy 0 keeps the synchronisation step's timesteps, policy 1 re-derives initial ones; with
+    softening the potential excludes the self pair."""
+    import importlib
+    pkg = importlib.import_module("26al-nbody_b200")
+    n = 200
+    c = pkg.ic.cluster(n, seed=3, require_massive=False)
+    p = [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
+    out = {}
+    for policy in (0, 1):
+        o = H.HermiteOracle(n); o.commit(*p); o.set_reinit_policy(policy)
+        o.evolve(0.01)
+        dt_sync = o.get_timesteps()[1].copy()
+        o.set_mass(p[0] * 0.95)
+        o.initialize()
+        dt_now = o.get_timesteps()[1]
+        if policy == 0:
+            assert np.array_equal(dt_now, dt_sync)
+        else:
+            assert np.all(dt_now <= 2.0 ** -5) and not np.array_equal(dt_now, dt_sync)
+        out[policy] = o.evolve(0.02)
+    assert out[0][0] < out[1][0]  # keeping the timesteps saves the climb back up the ladder
+    pot = H.force(*p, eps2=0.01)[6]
+    i = 7
+    want = -sum(p[0][j] / np.sqrt((p[1][i] - p[1][j]) ** 2 + (p[2][i] - p[2][j]) ** 2 + (p[3][i] - p[3][j]) ** 2 + 0.01)
+                for j in range(n) if j != i)
+    assert pot[i] == pytest.approx(want, rel=1e-13)
