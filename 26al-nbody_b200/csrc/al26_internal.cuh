@@ -257,12 +257,16 @@ int energy_grid(int n_loc);
 // enrichment (K5)
 constexpr int ENR_NINV = 8;
 constexpr int ENR_MAX_SOURCES = 8192;
+constexpr int ENR_GRID_MAX = 32;                                           // mode 2: cells per dimension at most
+constexpr int ENR_GRID_CELLS = ENR_GRID_MAX * ENR_GRID_MAX * ENR_GRID_MAX;
+constexpr int ENR_NCOUNTERS = 16;
 struct EnrichDev {
   int n_tot;      // global star count (classification, source table)
   int d0, n_loc;  // this rank's disc slice [d0, d0 + n_loc)
-  // replicated per-star inputs (global length)
+  // per-star inputs: mass always global length; mdot global length or (sliced upload) unused
   const double *mass_msun, *mdot;
   const double *px, *py, *pz, *pvx, *pvy, *pvz;  // km, km/s  (explicit arrays) or null
+  int pv_off;                                    // the explicit arrays start at this global index (0, or d0 when only the slice was uploaded)
   const double4 *gpos, *gvel;                    // gravity snapshot (global), used when px == null
   double km_per_length, kms_per_speed;
   const double *wr26, *wr60, *sn26, *sn60;       // global length
@@ -272,10 +276,18 @@ struct EnrichDev {
   uint8_t *alive;
   double *inv, *fin;  // [8][n_loc]
   // scratch
-  int *hm_list;       // [ENR_MAX_SOURCES]
-  int *counters;      // [0] n_hm, [1] n_events, [2] overflow flag
+  int *hm_list;       // [ENR_MAX_SOURCES] massive stars, ascending index after the sort
+  int *counters;      // [0] massive stars found, [1] n_events, [2] capacity flag, [3] n_hm (sorted list), [4] CTAs done,
+                      // [5..7] grid cells per dimension (mode 2)
   double4 *src_a;     // {x, y, z, c26}
   double4 *src_b;     // {c60, sn26, sn60, is_event}
+  double4 *src_f;     // fast test: {-2 x', -2 y', -2 z', |s'|^2 - q}, positions relative to fsum[2..4]
+  double4 *ev_a;      // this step's supernovae, ascending: {x, y, z, sn26}
+  double *ev_b;       //                                     sn60
+  double *fsum;       // [0] sum c26, [1] sum c60, [2..4] origin of the fast test, [5..7] grid corner, [8] 1 / cell size
+  double *hm_rows;    // sliced upload: [mdot, x, y, z][ENR_MAX_SOURCES] of the listed massive stars, gathered by the host
+  int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] starts, then [ENR_GRID_CELLS + 1] scatter cursors
+  int *cell_items;    // [ENR_MAX_SOURCES] source numbers by cell
   int *sn_events;     // [ENR_MAX_SOURCES]
 };
 struct EnrichParams {
@@ -284,8 +296,10 @@ struct EnrichParams {
   double r_global3;
   double decay26, decay60;
   int with_agb;
+  int mode;  // 0 exact (reference order, every pair), 1 fast (hoisted global sum, 4-DP pair test), 2 fast + cell-grid pruning
 };
-int launch_enrich(const EnrichDev &e, const EnrichParams &p, cudaStream_t s);
+int launch_enrich(const EnrichDev &e, const EnrichParams &p, int sm_count, bool tables_only, cudaStream_t s, cudaError_t *err);
+int launch_enrich_classify(const EnrichDev &e, const EnrichParams &p, int sm_count, cudaStream_t s);
 
 // AGB interloper deposit (al26_nbody.py:985-1028, calc_intersection :1156-1190)
 struct InterloperParams {

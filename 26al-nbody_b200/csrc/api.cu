@@ -125,9 +125,12 @@ struct al26_ctx {
   double *e_glob = nullptr;     // device: mass, mdot, px..pvz (8 n), wr26, wr60, sn26, sn60 (4 n)
   double *e_loc = nullptr;      // device: r_disk, tau (2 nloc), inv (8 nloc), fin (8 nloc)
   uint8_t *e_flags = nullptr;   // device: kicked (n), alive (nloc)
-  int *e_ints = nullptr;        // device: counters[8], hm_list, sn_events
-  double4 *e_src = nullptr;     // device: src_a, src_b
-  int *h_events = nullptr;      // pinned [8 + ENR_MAX_SOURCES]
+  int *e_ints = nullptr;        // device: counters, hm_list, sn_events, cell_items, cell_start + cursors
+  double4 *e_src = nullptr;     // device: src_a, src_b, src_f, ev_a
+  double *e_dbl = nullptr;      // device: ev_b, fsum, hm_rows
+  int *h_events = nullptr;      // pinned [ENR_NCOUNTERS + ENR_MAX_SOURCES]
+  double *h_rows = nullptr;     // pinned [4][ENR_MAX_SOURCES]: mdot, x, y, z of the massive stars (sliced upload)
+  int enrich_mode = 0;          // 0 exact, 1 fast, 2 fast + pruned (al26_enrich_set_mode)
   double km_per_length = 1.0, kms_per_speed = 1.0;
 };
 
@@ -273,10 +276,10 @@ void free_gravity(al26_ctx *c) {
 }
 
 void free_enrich(al26_ctx *c) {
-  void *ptrs[] = {c->e_glob, c->e_loc, c->e_flags, c->e_ints, c->e_src};
+  void *ptrs[] = {c->e_glob, c->e_loc, c->e_flags, c->e_ints, c->e_src, c->e_dbl};
   for (void *p : ptrs)
     if (p) cudaFree(p);
-  c->e_glob = c->e_loc = nullptr;
+  c->e_glob = c->e_loc = c->e_dbl = nullptr;
   c->e_flags = nullptr;
   c->e_ints = nullptr;
   c->e_src = nullptr;
@@ -534,7 +537,8 @@ al26_ctx *al26_create(int device_id) {
             cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
             cudaMallocHost(&c->h_hdr, sizeof(GravHeader)) == cudaSuccess &&
             cudaMallocHost(&c->h_small, 16 * sizeof(double)) == cudaSuccess &&
-            cudaMallocHost(&c->h_events, (8 + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
+            cudaMallocHost(&c->h_events, (ENR_NCOUNTERS + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
+            cudaMallocHost(&c->h_rows, 4 * ENR_MAX_SOURCES * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&c->en_out, 4 * sizeof(double)) == cudaSuccess && force_kernel_setup() == cudaSuccess &&
             loop_kernel_setup() == cudaSuccess;
   if (!ok) {
@@ -564,6 +568,7 @@ void al26_destroy(al26_ctx *c) {
   if (c->h_hdr) cudaFreeHost(c->h_hdr);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_events) cudaFreeHost(c->h_events);
+  if (c->h_rows) cudaFreeHost(c->h_rows);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -1439,19 +1444,29 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   CU(cudaMalloc(&c->e_glob, 12 * nt * sizeof(double)));
   CU(cudaMalloc(&c->e_loc, 20 * nl * sizeof(double)));  // r_disk, tau, inv[8], fin[8], agb_raw[2]
   CU(cudaMalloc(&c->e_flags, nt + nl));
-  CU(cudaMalloc(&c->e_ints, (8 + 2 * ENR_MAX_SOURCES) * sizeof(int)));
-  CU(cudaMalloc(&c->e_src, 2 * ENR_MAX_SOURCES * sizeof(double4)));
+  const size_t n_ints = ENR_NCOUNTERS + 3 * (size_t)ENR_MAX_SOURCES + 2 * ((size_t)ENR_GRID_CELLS + 1);
+  CU(cudaMalloc(&c->e_ints, n_ints * sizeof(int)));
+  CU(cudaMemsetAsync(c->e_ints, 0, n_ints * sizeof(int), c->stream));
+  CU(cudaMalloc(&c->e_src, 4 * ENR_MAX_SOURCES * sizeof(double4)));
+  CU(cudaMalloc(&c->e_dbl, (5 * (size_t)ENR_MAX_SOURCES + 16) * sizeof(double)));
   EnrichDev &e = c->e;
   e.n_tot = (int)n; e.d0 = (int)d0; e.n_loc = (int)nloc;
   double *G = c->e_glob;
   e.mass_msun = G; e.mdot = G + nt;
   e.px = nullptr; e.py = e.pz = e.pvx = e.pvy = e.pvz = nullptr;
+  e.pv_off = 0;
   e.wr26 = G + 8 * nt; e.wr60 = G + 9 * nt; e.sn26 = G + 10 * nt; e.sn60 = G + 11 * nt;
   double *Lc = c->e_loc;
   e.r_disk = Lc; e.tau_disk = Lc + nl; e.inv = Lc + 2 * nl; e.fin = Lc + 10 * nl;
   e.kicked = c->e_flags; e.alive = c->e_flags + nt;
-  e.counters = c->e_ints; e.hm_list = c->e_ints + 8; e.sn_events = c->e_ints + 8 + ENR_MAX_SOURCES;
-  e.src_a = c->e_src; e.src_b = c->e_src + ENR_MAX_SOURCES;
+  e.counters = c->e_ints;
+  e.hm_list = c->e_ints + ENR_NCOUNTERS;
+  e.sn_events = e.hm_list + ENR_MAX_SOURCES;
+  e.cell_items = e.sn_events + ENR_MAX_SOURCES;
+  e.cell_start = e.cell_items + ENR_MAX_SOURCES;
+  e.src_a = c->e_src; e.src_b = c->e_src + ENR_MAX_SOURCES; e.src_f = c->e_src + 2 * ENR_MAX_SOURCES;
+  e.ev_a = c->e_src + 3 * ENR_MAX_SOURCES;
+  e.ev_b = c->e_dbl; e.fsum = c->e_dbl + ENR_MAX_SOURCES; e.hm_rows = c->e_dbl + ENR_MAX_SOURCES + 16;
   CU(cudaMemcpyAsync(G + 8 * nt, wr26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(G + 9 * nt, wr60, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(G + 10 * nt, sn26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1488,6 +1503,13 @@ int al26_enrich_set_units(al26_ctx *c, double km_per_length, double kms_per_spee
   return 0;
 }
 
+int al26_enrich_set_mode(al26_ctx *c, int mode) {
+  if (!c) return AL26_EINVAL;
+  if (mode < 0 || mode > 2) return fail(c, AL26_EINVAL, "enrichment mode must be 0 (exact), 1 (fast) or 2 (fast, pruned)");
+  c->enrich_mode = mode;
+  return 0;
+}
+
 int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const double *mdot, const double *pos_vel,
                      double dt_s, double t_new_myr, double r_bub_local_km, double r_bub_global_km, double decay26,
                      double decay60, int with_agb, int32_t *sn_events, int64_t sn_cap, int64_t *n_sn_events) {
@@ -1504,23 +1526,6 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
   const size_t nt = (size_t)n;
   EnrichDev &e = c->e;
   double *G = c->e_glob;
-  CU(cudaMemcpyAsync(G, mass_msun, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(G + nt, mdot, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (pos_vel) {
-    CU(cudaMemcpyAsync(G + 2 * nt, pos_vel, 6 * nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    e.px = G + 2 * nt; e.py = G + 3 * nt; e.pz = G + 4 * nt;
-    e.pvx = G + 5 * nt; e.pvy = G + 6 * nt; e.pvz = G + 7 * nt;
-    e.gpos = e.gvel = nullptr;
-  } else {
-    c->launches += launch_snapshot_j(c->g, c->stream);
-    int rc = gather_j(c);
-    if (rc) return rc;
-    e.px = e.py = e.pz = e.pvx = e.pvy = e.pvz = nullptr;
-    e.gpos = c->g.jpos;
-    e.gvel = c->g.jvel;
-    e.km_per_length = c->km_per_length;
-    e.kms_per_speed = c->kms_per_speed;
-  }
   EnrichParams p;
   p.dt_s = dt_s; p.t_new_myr = t_new_myr;
   p.r_local = r_bub_local_km;
@@ -1531,13 +1536,70 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
   while (sqrt(q) >= r_bub_local_km) q = nextafter(q, -INFINITY);
   while (sqrt(q) < r_bub_local_km) q = nextafter(q, INFINITY);
   p.q_local = q;
-  p.decay26 = decay26; p.decay60 = decay60; p.with_agb = with_agb;
-  CU(cudaMemsetAsync(e.counters, 0, 8 * sizeof(int), c->stream));
+  p.decay26 = decay26; p.decay60 = decay60; p.with_agb = with_agb; p.mode = c->enrich_mode;
+  CU(cudaMemsetAsync(e.counters, 0, ENR_NCOUNTERS * sizeof(int), c->stream));
+  CU(cudaMemcpyAsync(G, mass_msun, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // Several ranks, explicit positions: every rank needs all N masses (classification) but only ITS discs' kinematics
+  // and the massive stars' rows -- classify on the device, read the (short, sorted) list back, gather those stars'
+  // mdot / x / y / z on the host (an index gather, no arithmetic) and upload them with the slice:
+  // 8 N + 48 N / P bytes per rank instead of 64 N.
+  const bool sliced = pos_vel && c->world > 1;
+  bool tables_only = false;
+  float ms_cls = 0.f;
+  if (sliced) {
+    CU(cudaEventRecord(c->ev2, c->stream));
+    c->launches += launch_enrich_classify(e, p, c->sm_count, c->stream);
+    CU(cudaEventRecord(c->ev3, c->stream));
+    CU(cudaMemcpyAsync(c->h_events, e.counters, ENR_NCOUNTERS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_events + ENR_NCOUNTERS, e.hm_list, ENR_MAX_SOURCES * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&ms_cls, c->ev2, c->ev3));
+    if (c->h_events[0] > ENR_MAX_SOURCES) return fail(c, AL26_ECAP, "more than %d massive stars", ENR_MAX_SOURCES);
+    const int n_hm = c->h_events[3];
+    const int *list = c->h_events + ENR_NCOUNTERS;
+    for (int k = 0; k < n_hm; k++) {
+      const size_t i = (size_t)list[k];
+      c->h_rows[k] = mdot[i];
+      for (int d = 0; d < 3; d++) c->h_rows[(size_t)(d + 1) * ENR_MAX_SOURCES + k] = pos_vel[(size_t)d * nt + i];
+    }
+    if (n_hm > 0)
+      for (int r = 0; r < 4; r++)
+        CU(cudaMemcpyAsync(e.hm_rows + (size_t)r * ENR_MAX_SOURCES, c->h_rows + (size_t)r * ENR_MAX_SOURCES,
+                           (size_t)n_hm * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const size_t nl = (size_t)e.n_loc;
+    for (int r = 0; r < 6; r++)
+      CU(cudaMemcpyAsync(G + (2 + r) * nt, pos_vel + (size_t)r * nt + e.d0, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    e.px = G + 2 * nt; e.py = G + 3 * nt; e.pz = G + 4 * nt;
+    e.pvx = G + 5 * nt; e.pvy = G + 6 * nt; e.pvz = G + 7 * nt;
+    e.pv_off = e.d0;
+    e.gpos = e.gvel = nullptr;
+    tables_only = true;
+  } else {
+    CU(cudaMemcpyAsync(G + nt, mdot, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    e.pv_off = 0;
+    if (pos_vel) {
+      CU(cudaMemcpyAsync(G + 2 * nt, pos_vel, 6 * nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      e.px = G + 2 * nt; e.py = G + 3 * nt; e.pz = G + 4 * nt;
+      e.pvx = G + 5 * nt; e.pvy = G + 6 * nt; e.pvz = G + 7 * nt;
+      e.gpos = e.gvel = nullptr;
+    } else {
+      c->launches += launch_snapshot_j(c->g, c->stream);
+      int rc = gather_j(c);
+      if (rc) return rc;
+      e.px = e.py = e.pz = e.pvx = e.pvy = e.pvz = nullptr;
+      e.gpos = c->g.jpos;
+      e.gvel = c->g.jvel;
+      e.km_per_length = c->km_per_length;
+      e.kms_per_speed = c->kms_per_speed;
+    }
+  }
   CU(cudaEventRecord(c->ev2, c->stream));
-  c->launches += launch_enrich(e, p, c->stream);
+  cudaError_t le = cudaSuccess;
+  c->launches += launch_enrich(e, p, c->sm_count, tables_only, c->stream, &le);
+  if (le != cudaSuccess) return fail(c, AL26_ECUDA, "enrichment launch failed: %s", cudaGetErrorString(le));
   CU(cudaEventRecord(c->ev3, c->stream));
-  CU(cudaMemcpyAsync(c->h_events, e.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_events + 8, e.sn_events, ENR_MAX_SOURCES * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_events, e.counters, ENR_NCOUNTERS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_events + ENR_NCOUNTERS, e.sn_events, ENR_MAX_SOURCES * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaGetLastError());
@@ -1545,14 +1607,15 @@ int al26_enrich_step(al26_ctx *c, int64_t n, const double *mass_msun, const doub
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   CU(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
-  c->last_kernel_ms = ms;
+  c->last_kernel_ms = ms + ms_cls;
   c->last_launches = c->launches - l0;
+  // capacity: detected by the source kernel BEFORE anything was mutated (the disc kernel returned at once)
   if (c->h_events[2]) return fail(c, AL26_ECAP, "more than %d massive stars", ENR_MAX_SOURCES);
   const int ne = c->h_events[1];
   if (n_sn_events) *n_sn_events = ne;
   if (ne > 0) {
     if (!sn_events || sn_cap < ne) return fail(c, AL26_ECAP, "%d supernova events exceed sn_cap %lld", ne, (long long)sn_cap);
-    memcpy(sn_events, c->h_events + 8, (size_t)ne * sizeof(int));
+    memcpy(sn_events, c->h_events + ENR_NCOUNTERS, (size_t)ne * sizeof(int));
   }
   return 0;
 }

@@ -2,44 +2,49 @@
 // /root/reference/al26_nbody.py:878-1086 (interloper block excluded):
 //   classify (:1194-1216) -> wind deposit, local + global bubble, 26Al + 60Fe (:642-702, :897-938)
 //   -> supernova events + deposit (:945-967, :1326-1334) -> decay (:1048-1064) -> condense (:1071-1086).
-// Compiled with --fmad=false and written in the reference's evaluation order, so the per-disc
-// wind sums are BIT-IDENTICAL to the reference's numba kernel: per disc the massive stars are
-// visited in ascending index order (the sorted source table), each term is
-// ((wind_ratio*mdot)*eta_bub)*dt with eta_bub = ((0.75*(r*r))*d_trav)/(R*(R*R)).
-// The reference evaluates the geometry four times per step (once per calc_wind_abs call); here
-// it is evaluated once per (disc, source) pair and feeds all four accumulators.
+// Compiled with --fmad=false and written in the reference's evaluation order: per disc the massive stars are
+// visited in ascending index order (the sorted source table), each wind term is
+// ((wind_ratio*mdot)*eta_bub)*dt with eta_bub = ((0.75*(r*r))*d_trav)/(R*(R*R)).  The reference evaluates the
+// geometry four times per step (once per calc_wind_abs call); here once per (disc, source) pair.
 //
-// Kernels (3 launches per outer step):
-//   k_enrich_classify  all stars: m >= 13 Msun -> atomic append to the source list
-//   k_enrich_sources   one CTA: bitonic sort of the list (ascending index), build the source
-//                      table {x,y,z,c26},{c60,sn26,sn60,event}, detect SN events (mdot == 0 and
-//                      not kicked), set kicked, emit the ordered event list
-//   k_enrich_discs     one thread per star of this rank's slice: source loop from shared memory
-//                      (broadcast reads), decay of all rows, condense flags; FP64-issue bound
-//                      for many sources, HBM bound (~260 B per disc-update) for few.
+// Two launches per outer step:
+//   k_enrich_sources   all stars: m >= 13 Msun -> atomic append to the source list; the LAST CTA to finish sorts the
+//                      list (ascending index = the reference's summation order), builds the source table
+//                      {x,y,z,c26},{c60,sn26,sn60,event}, detects SN events (mdot == 0 and not kicked), sets kicked,
+//                      emits the ordered event list, and (fast modes) the hoisted sums / the fast-test table / the cell
+//                      grid.  More than ENR_MAX_SOURCES massive stars: flag raised, NOTHING is mutated (the disc kernel
+//                      returns at once), the call fails with AL26_ECAP and the state is what it was.
+//   k_enrich_discs<M>  one thread per star of this rank's slice, launched with programmatic stream serialization: all
+//                      of the star's loads (inventories, kinematics, disc, flags -- the HBM traffic of the step) are
+//                      issued before griddepcontrol.wait, i.e. while the source table is still being built; then the
+//                      source loop, decay of all rows, condense flags.
+// Modes (al26_enrich_set_mode):
+//   0 exact   every (disc, source) pair in the reference's order: wind sums BIT-IDENTICAL to the reference's numba
+//             kernel.  15 DP instructions per pair (6 of them the separable global model).
+//   1 fast    tolerance mode (north_star: per-disc masses within 1e-10): the global model is separable, so its source
+//             sum is hoisted into k_enrich_sources (relative difference ~1e-13: summation order); the local-bubble
+//             test runs on |x|^2 - 2 s.x + (|s|^2 - q) < 0 with the source part precomputed: 3 DFMA + 1 DSETP per
+//             pair.  Local deposits (same terms, same ascending order) and SN deposits (exact difference form over
+//             the event list) stay bit-identical unless a pair sits within ~1e-12 (relative) of the bubble surface.
+//   2 pruned  as 1, but the local-bubble candidates come from a uniform cell grid over the sources (cell >= bubble
+//             radius, <= 32^3 cells, 27-cell neighbourhood) and are tested in the exact difference form: local rows
+//             bit-identical to mode 0, the pair loop is gone, the kernel is HBM-bound at any source count.
 #include "al26_internal.cuh"
 
 namespace al26 {
 
 constexpr int EN_T = 256;
+constexpr int SRC_T = 1024;     // threads of k_enrich_sources
 constexpr int SRC_TILE = 512;   // sources staged per shared-memory tile (2 x 16 KB)
+constexpr int MATCH_CAP = 12;   // mode 2: local-bubble hits kept per disc before falling back to the full scan
 
-__global__ void __launch_bounds__(EN_T) k_enrich_classify(const EnrichDev e) {
-  const int i = blockIdx.x * EN_T + threadIdx.x;
-  if (i == 0) {
-    e.counters[1] = 0;
-  }
-  if (i >= e.n_tot) return;
-  if (e.mass_msun[i] >= 13.0) {
-    const int p = atomicAdd(&e.counters[0], 1);
-    if (p < ENR_MAX_SOURCES) e.hm_list[p] = i;
-    else e.counters[2] = 1;
-  }
-}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void star_pos(const EnrichDev &e, int i, double &x, double &y, double &z) {
   if (e.px) {
-    x = e.px[i]; y = e.py[i]; z = e.pz[i];
+    const int k = i - e.pv_off;
+    x = e.px[k]; y = e.py[k]; z = e.pz[k];
   } else {
     const double4 p = e.gpos[i];
     x = p.x * e.km_per_length; y = p.y * e.km_per_length; z = p.z * e.km_per_length;
@@ -47,86 +52,267 @@ __device__ __forceinline__ void star_pos(const EnrichDev &e, int i, double &x, d
 }
 __device__ __forceinline__ void star_vel(const EnrichDev &e, int i, double &x, double &y, double &z) {
   if (e.px) {
-    x = e.pvx[i]; y = e.pvy[i]; z = e.pvz[i];
+    const int k = i - e.pv_off;
+    x = e.pvx[k]; y = e.pvy[k]; z = e.pvz[k];
   } else {
     const double4 p = e.gvel[i];
     x = p.x * e.kms_per_speed; y = p.y * e.kms_per_speed; z = p.z * e.kms_per_speed;
   }
 }
 
-__global__ void __launch_bounds__(1024) k_enrich_sources(const EnrichDev e) {
-  __shared__ int keys[ENR_MAX_SOURCES];
-  int n_hm = e.counters[0];
-  if (n_hm > ENR_MAX_SOURCES) n_hm = ENR_MAX_SOURCES;
-  int np2 = 1;
-  while (np2 < n_hm) np2 <<= 1;
-  for (int k = threadIdx.x; k < np2; k += blockDim.x) keys[k] = (k < n_hm) ? e.hm_list[k] : 0x7fffffff;
+// fixed-order block sum (warp butterflies, then warp 0 over the warp totals in order); result valid in every thread
+__device__ __forceinline__ double block_sum_all(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
-  for (int size = 2; size <= np2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int k = threadIdx.x; k < np2; k += blockDim.x) {
-        const int partner = k ^ stride;
-        if (partner > k) {
-          const bool up = ((k & size) == 0);
-          const int a = keys[k], b = keys[partner];
-          if ((a > b) == up) {
-            keys[k] = b;
-            keys[partner] = a;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
+  return r;
+}
+__device__ __forceinline__ double block_min_all(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmin(r, sh[w]);
+  return r;
+}
+
+// phase 0: classify + tables; phase 1: classify + sort only (the host then gathers the massive stars' rows);
+// phase 2: tables only, from the compact per-source rows e.hm_rows = [mdot, x, y, z][ENR_MAX_SOURCES]
+__global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, const EnrichParams p, const int phase) {
+  __shared__ int keys[ENR_MAX_SOURCES];
+  __shared__ double shd[SRC_T / 32];
+  __shared__ int shi[SRC_T / 32 + 1];
+  __shared__ int is_last;
+  pdl_launch_dependents();  // the disc kernel may start its (source-independent) loads
+  const int tid = threadIdx.x;
+  if (phase != 2) {
+    for (int i = blockIdx.x * SRC_T + tid; i < e.n_tot; i += gridDim.x * SRC_T) {
+      if (e.mass_msun[i] >= 13.0) {
+        const int q = atomicAdd(&e.counters[0], 1);
+        if (q < ENR_MAX_SOURCES) e.hm_list[q] = i;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      is_last = (atomicAdd(&e.counters[4], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+  }
+  const int n_raw = (phase == 2) ? e.counters[3] : *(volatile int *)&e.counters[0];
+  if (n_raw > ENR_MAX_SOURCES) {  // capacity exceeded: raise the flag, mutate nothing
+    if (tid == 0) {
+      e.counters[2] = 1;
+      e.counters[1] = 0;
+      e.counters[3] = 0;
+    }
+    return;
+  }
+  const int n_hm = n_raw;
+  if (phase != 2) {
+    int np2 = 1;
+    while (np2 < n_hm) np2 <<= 1;
+    for (int k = tid; k < np2; k += SRC_T) keys[k] = (k < n_hm) ? __ldcg(&e.hm_list[k]) : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int k = tid; k < np2; k += SRC_T) {
+          const int partner = k ^ stride;
+          if (partner > k) {
+            const bool up = ((k & size) == 0);
+            const int a = keys[k], b = keys[partner];
+            if ((a > b) == up) {
+              keys[k] = b;
+              keys[partner] = a;
+            }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
+    }
+    for (int k = tid; k < n_hm; k += SRC_T) e.hm_list[k] = keys[k];
+    if (tid == 0) e.counters[3] = n_hm;
+    if (phase == 1) return;
+  } else {
+    for (int k = tid; k < n_hm; k += SRC_T) keys[k] = e.hm_list[k];
+    __syncthreads();
+  }
+
+  // ---- source table; origin of the fast test = the first source (keeps |x'| at cluster scale) ----
+  double ox = 0.0, oy = 0.0, oz = 0.0;
+  if (n_hm > 0) {
+    if (phase == 2) {
+      ox = e.hm_rows[1 * ENR_MAX_SOURCES]; oy = e.hm_rows[2 * ENR_MAX_SOURCES]; oz = e.hm_rows[3 * ENR_MAX_SOURCES];
+    } else {
+      star_pos(e, keys[0], ox, oy, oz);
     }
   }
-  for (int k = threadIdx.x; k < n_hm; k += blockDim.x) {
+  double s26 = 0.0, s60 = 0.0;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int k = tid; k < n_hm; k += SRC_T) {
     const int i = keys[k];
-    e.hm_list[k] = i;
-    double x, y, z;
-    star_pos(e, i, x, y, z);
-    const double mdot = e.mdot[i];
+    double x, y, z, mdot;
+    if (phase == 2) {
+      mdot = e.hm_rows[k];
+      x = e.hm_rows[1 * ENR_MAX_SOURCES + k]; y = e.hm_rows[2 * ENR_MAX_SOURCES + k]; z = e.hm_rows[3 * ENR_MAX_SOURCES + k];
+    } else {
+      star_pos(e, i, x, y, z);
+      mdot = e.mdot[i];
+    }
     const bool ev = (mdot == 0.0) && (e.kicked[i] == 0);
-    e.src_a[k] = make_double4(x, y, z, e.wr26[i] * mdot);
-    e.src_b[k] = make_double4(e.wr60[i] * mdot, ev ? e.sn26[i] : 0.0, ev ? e.sn60[i] : 0.0, ev ? 1.0 : 0.0);
+    const double c26 = e.wr26[i] * mdot, c60 = e.wr60[i] * mdot;
+    e.src_a[k] = make_double4(x, y, z, c26);
+    e.src_b[k] = make_double4(c60, ev ? e.sn26[i] : 0.0, ev ? e.sn60[i] : 0.0, ev ? 1.0 : 0.0);
+    const double xs = x - ox, ys = y - oy, zs = z - oz;
+    e.src_f[k] = make_double4(-2.0 * xs, -2.0 * ys, -2.0 * zs, (xs * xs + ys * ys + zs * zs) - p.q_local);
+    s26 += c26;
+    s60 += c60;
+    lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z);
+    hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
+  }
+  s26 = block_sum_all(s26, shd);
+  s60 = block_sum_all(s60, shd);
+  __syncthreads();  // src_b is complete (block_sum_all's barriers) -- the event scan below reads it back
+
+  // ---- ordered SN event list (ascending index), kicked, event table ----
+  int base = 0;
+  for (int k0 = 0; k0 < n_hm; k0 += SRC_T) {
+    const int k = k0 + tid;
+    const bool ev = (k < n_hm) && (e.src_b[k].w != 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, ev);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) shi[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; w++) off += shi[w];
+    if (ev) {
+      const int slot = off + __popc(m & ((1u << lane) - 1u));
+      const int i = keys[k];
+      e.sn_events[slot] = i;
+      e.kicked[i] = 1;
+      const double4 A = e.src_a[k], B = e.src_b[k];
+      e.ev_a[slot] = make_double4(A.x, A.y, A.z, B.y);
+      e.ev_b[slot] = B.z;
+    }
+    int tot = 0;
+    for (int w = 0; w < SRC_T / 32; w++) tot += shi[w];
+    base += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    e.counters[1] = base;
+    e.fsum[0] = s26; e.fsum[1] = s60;
+    e.fsum[2] = ox; e.fsum[3] = oy; e.fsum[4] = oz;
+  }
+  if (p.mode != 2) return;
+
+  // ---- mode 2: uniform cell grid over the sources' bounding box; cell size >= the local bubble radius ----
+  for (int c = 0; c < 3; c++) {
+    lo[c] = block_min_all(lo[c], shd);
+    hi[c] = -block_min_all(-hi[c], shd);
+  }
+  int gd[3] = {1, 1, 1};
+  double h = p.r_local * (1.0 + 1e-6);
+  if (n_hm > 0) {
+    const double ext = fmax(hi[0] - lo[0], fmax(hi[1] - lo[1], hi[2] - lo[2]));
+    h = fmax(h, ext / (double)ENR_GRID_MAX * (1.0 + 1e-9));
+    for (int c = 0; c < 3; c++) {
+      int g = (int)floor((hi[c] - lo[c]) / h) + 1;
+      gd[c] = g < 1 ? 1 : (g > ENR_GRID_MAX ? ENR_GRID_MAX : g);
+    }
+  } else {
+    lo[0] = lo[1] = lo[2] = 0.0;
+  }
+  const double inv_h = 1.0 / h;
+  const int ncell = gd[0] * gd[1] * gd[2];
+  int *start = e.cell_start, *cursor = e.cell_start + (ENR_GRID_CELLS + 1);
+  for (int c = tid; c <= ncell; c += SRC_T) start[c] = 0;
+  __syncthreads();
+  for (int k = tid; k < n_hm; k += SRC_T) {
+    const double4 A = e.src_a[k];
+    int cx = (int)floor((A.x - lo[0]) * inv_h), cy = (int)floor((A.y - lo[1]) * inv_h), cz = (int)floor((A.z - lo[2]) * inv_h);
+    cx = min(max(cx, 0), gd[0] - 1); cy = min(max(cy, 0), gd[1] - 1); cz = min(max(cz, 0), gd[2] - 1);
+    atomicAdd(&start[(cz * gd[1] + cy) * gd[0] + cx + 1], 1);  // counts shifted by one: the scan leaves starts
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int ne = 0;
-    for (int k = 0; k < n_hm; k++) {
-      if (e.src_b[k].w != 0.0) {
-        const int i = keys[k];
-        e.sn_events[ne++] = i;
-        e.kicked[i] = 1;
-      }
+  {  // inclusive scan of start[1..ncell] in place (each thread a contiguous run, then the block's run totals)
+    const int per = (ncell + SRC_T - 1) / SRC_T;
+    const int b = 1 + tid * per, en = min(ncell + 1, b + per);
+    int run = 0;
+    for (int c = b; c < en; c++) run += start[c];
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    e.counters[1] = ne;
-    e.counters[3] = n_hm;
+    if (lane == 31) shi[warp] = incl;
+    __syncthreads();
+    int off = incl - run;
+    for (int w = 0; w < warp; w++) off += shi[w];
+    for (int c = b; c < en; c++) {
+      off += start[c];
+      start[c] = off;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += SRC_T) cursor[c] = start[c];
+  __syncthreads();
+  for (int k = tid; k < n_hm; k += SRC_T) {
+    const double4 A = e.src_a[k];
+    int cx = (int)floor((A.x - lo[0]) * inv_h), cy = (int)floor((A.y - lo[1]) * inv_h), cz = (int)floor((A.z - lo[2]) * inv_h);
+    cx = min(max(cx, 0), gd[0] - 1); cy = min(max(cy, 0), gd[1] - 1); cz = min(max(cz, 0), gd[2] - 1);
+    e.cell_items[atomicAdd(&cursor[(cz * gd[1] + cy) * gd[0] + cx], 1)] = k;
+  }
+  if (tid == 0) {
+    e.counters[5] = gd[0]; e.counters[6] = gd[1]; e.counters[7] = gd[2];
+    e.fsum[5] = lo[0]; e.fsum[6] = lo[1]; e.fsum[7] = lo[2]; e.fsum[8] = inv_h;
   }
 }
 
+// one thread per star.  MODE: see the file header.
+template <int MODE>
 __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const EnrichParams p) {
   __shared__ double4 sa[SRC_TILE];
   __shared__ double4 sb[SRC_TILE];
   const int li = blockIdx.x * EN_T + threadIdx.x;
   const bool valid = li < e.n_loc;
   const int gi = e.d0 + (valid ? li : 0);
-  int n_hm = e.counters[0];
-  if (n_hm > ENR_MAX_SOURCES) n_hm = ENR_MAX_SOURCES;
-  const int n_ev = e.counters[1];
-
-  const double m = valid ? e.mass_msun[gi] : 0.0;
-  const bool is_lm = valid && (m >= 0.1) && (m <= 3.0);
+  const int lj = valid ? li : 0;
   const size_t n = (size_t)e.n_loc;
+  const bool agb = p.with_agb != 0;
 
+  // ---- every load of this star up front: one memory round trip, none of it depends on the source kernel ----
+  const double m = e.mass_msun[gi];
   double inv[ENR_NINV];
 #pragma unroll
-  for (int r = 0; r < ENR_NINV; r++) inv[r] = valid ? e.inv[r * n + li] : 0.0;
+  for (int r = 0; r < ENR_NINV; r++) inv[r] = (agb || (r != 3 && r != 7)) ? e.inv[r * n + lj] : 0.0;
+  double x, y, z, vx, vy, vz;
+  star_pos(e, gi, x, y, z);
+  star_vel(e, gi, vx, vy, vz);
+  const double rd = e.r_disk[lj];
+  const double tau = e.tau_disk[lj];
+  const uint8_t was_alive = e.alive[lj];
 
-  double x = 0, y = 0, z = 0, rd = 0, eta_l = 0, eta_g = 0;
+  pdl_wait_primary();  // the source table, counters and event list are complete and visible
+  if (e.counters[2] != 0) return;  // capacity exceeded: the call fails, nothing may change
+  const int n_hm = e.counters[3];
+  const int n_ev = e.counters[1];
+  const bool is_lm = valid && (m >= 0.1) && (m <= 3.0);
+
+  double eta_l = 0.0, eta_g = 0.0;
   if (is_lm && n_hm > 0) {
-    double vx, vy, vz;
-    star_pos(e, gi, x, y, z);
-    star_vel(e, gi, vx, vy, vz);
-    rd = e.r_disk[li];
     const double spd = sqrt(vx * vx + vy * vy + vz * vz);   // (lm_vx**2 + lm_vy**2 + lm_vz**2)**0.5
     const double trav = spd * p.dt_s;                       // d_disk_trav = disk_spd * dt
     const double k0 = 0.75 * (rd * rd) * trav;              // 0.75 * (r_disk**2) * d_disk_trav
@@ -136,47 +322,163 @@ __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const 
   double l26 = 0.0, l60 = 0.0, g26 = 0.0, g60 = 0.0;
   double s26 = inv[2], s60 = inv[6];  // SN deposits add straight onto the inventories (:964-965)
 
-  for (int b = 0; b < n_hm; b += SRC_TILE) {
-    const int cnt = min(SRC_TILE, n_hm - b);
-    __syncthreads();
-    for (int k = threadIdx.x; k < cnt; k += EN_T) {
-      sa[k] = e.src_a[b + k];
-      sb[k] = e.src_b[b + k];
-    }
-    __syncthreads();
-    if (is_lm) {
-      // Sources in groups of 64: the hot loop only MARKS the sources whose local bubble holds this disc (a predicated
-      // integer OR) -- their deposit, 6 DP instructions that predication would otherwise issue for every pair, is
-      // added afterwards for the marked ones only (rare: R = 0.1 pc in a ~1 pc cluster), still in ascending source
-      // order, so the sums keep the reference's rounding.
-      for (int k0 = 0; k0 < cnt; k0 += 64) {
-        const int gn = min(64, cnt - k0);
-        unsigned long long marked = 0ull;
+  if (MODE == 0) {
+    for (int b = 0; b < n_hm; b += SRC_TILE) {
+      const int cnt = min(SRC_TILE, n_hm - b);
+      __syncthreads();
+      for (int k = threadIdx.x; k < cnt; k += EN_T) {
+        sa[k] = e.src_a[b + k];
+        sb[k] = e.src_b[b + k];
+      }
+      __syncthreads();
+      if (is_lm) {
+        // Sources in groups of 64: the hot loop only MARKS the sources whose local bubble holds this disc (a predicated
+        // integer OR) -- their deposit, 6 DP instructions that predication would otherwise issue for every pair, is
+        // added afterwards for the marked ones only (rare: R = 0.1 pc in a ~1 pc cluster), still in ascending source
+        // order, so the sums keep the reference's rounding.
+        for (int k0 = 0; k0 < cnt; k0 += 64) {
+          const int gn = min(64, cnt - k0);
+          unsigned long long marked = 0ull;
 #pragma unroll 4
-        for (int kk = 0; kk < gn; kk++) {
-          const double4 A = sa[k0 + kk];
-          const double4 B = sb[k0 + kk];
-          // global model: distance_limit == 0 -> no test (:688)
-          g26 += (A.w * eta_g) * p.dt_s;
-          g60 += (B.x * eta_g) * p.dt_s;
-          // local model: skip when bubble_radius <= d_sep (:689-691); q_local is the exact
-          // d^2 threshold of that test, so no sqrt is needed here
-          const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
-          const double d2 = dx * dx + dy * dy + dz * dz;
-          if (!(d2 >= p.q_local)) marked |= 1ull << kk;
-          if (n_ev > 0 && B.w != 0.0) {
-            // calc_star_distance + calc_eta_disk_sne (:1331-1333)
-            const double d = sqrt(d2);
-            const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
-            s26 += B.y * eta;
-            s60 += B.z * eta;
+          for (int kk = 0; kk < gn; kk++) {
+            const double4 A = sa[k0 + kk];
+            const double4 B = sb[k0 + kk];
+            // global model: distance_limit == 0 -> no test (:688)
+            g26 += (A.w * eta_g) * p.dt_s;
+            g60 += (B.x * eta_g) * p.dt_s;
+            // local model: skip when bubble_radius <= d_sep (:689-691); q_local is the exact
+            // d^2 threshold of that test, so no sqrt is needed here
+            const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (!(d2 >= p.q_local)) marked |= 1ull << kk;
+            if (n_ev > 0 && B.w != 0.0) {
+              // calc_star_distance + calc_eta_disk_sne (:1331-1333)
+              const double d = sqrt(d2);
+              const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
+              s26 += B.y * eta;
+              s60 += B.z * eta;
+            }
+          }
+          while (marked) {
+            const int kk = __ffsll((long long)marked) - 1;
+            marked &= marked - 1ull;
+            l26 += (sa[k0 + kk].w * eta_l) * p.dt_s;
+            l60 += (sb[k0 + kk].x * eta_l) * p.dt_s;
           }
         }
-        while (marked) {
-          const int kk = __ffsll((long long)marked) - 1;
-          marked &= marked - 1ull;
-          l26 += (sa[k0 + kk].w * eta_l) * p.dt_s;
-          l60 += (sb[k0 + kk].x * eta_l) * p.dt_s;
+      }
+    }
+  } else {
+    // ---- fast modes: hoisted global sum; SN deposits over the (short, ordered) event list in the exact form ----
+    if (is_lm && n_hm > 0) {
+      g26 = (e.fsum[0] * eta_g) * p.dt_s;
+      g60 = (e.fsum[1] * eta_g) * p.dt_s;
+      for (int q = 0; q < n_ev; q++) {
+        const double4 A = e.ev_a[q];
+        const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        const double eta = (0.5 * 0.7) * ((0.5 * (rd * rd)) / (4.0 * (d * d)));
+        s26 += A.w * eta;
+        s60 += e.ev_b[q] * eta;
+      }
+    }
+    bool full_scan = (MODE == 1);
+    if (MODE == 2 && is_lm && n_hm > 0) {
+      const int gx = e.counters[5], gy = e.counters[6], gz = e.counters[7];
+      const double inv_h = e.fsum[8];
+      const double ux = fmin(fmax((x - e.fsum[5]) * inv_h, -4.0), 64.0), uy = fmin(fmax((y - e.fsum[6]) * inv_h, -4.0), 64.0),
+                   uz = fmin(fmax((z - e.fsum[7]) * inv_h, -4.0), 64.0);
+      const int cx = (int)floor(ux), cy = (int)floor(uy), cz = (int)floor(uz);
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gx - 1);
+      int hits[MATCH_CAP];
+      int nh = 0;
+      if (x0 <= x1) {
+        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, gz - 1); zz++) {
+          for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); yy++) {
+            const int row = (zz * gy + yy) * gx;
+            const int tb = __ldg(&e.cell_start[row + x0]), te = __ldg(&e.cell_start[row + x1 + 1]);
+            for (int t = tb; t < te; t++) {
+              const int k = __ldg(&e.cell_items[t]);
+              const double4 A = e.src_a[k];
+              const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+              const double d2 = dx * dx + dy * dy + dz * dz;
+              if (!(d2 >= p.q_local)) {
+                if (nh < MATCH_CAP) hits[nh] = k;
+                nh++;
+              }
+            }
+          }
+        }
+      }
+      if (nh > MATCH_CAP) {
+        full_scan = true;  // a disc inside more bubbles than the hit list holds: take the all-pairs scan for it
+      } else {
+        for (int a = 1; a < nh; a++) {  // ascending source order = the reference's summation order
+          const int v = hits[a];
+          int b = a - 1;
+          while (b >= 0 && hits[b] > v) {
+            hits[b + 1] = hits[b];
+            b--;
+          }
+          hits[b + 1] = v;
+        }
+        for (int a = 0; a < nh; a++) {
+          l26 += (e.src_a[hits[a]].w * eta_l) * p.dt_s;
+          l60 += (e.src_b[hits[a]].x * eta_l) * p.dt_s;
+        }
+      }
+    }
+    if (MODE == 1) {
+      // all pairs, 3 DFMA + 1 DSETP each: d^2 - q = |x'|^2 + (-2 s'.x' + |s'|^2 - q), positions relative to the origin
+      const double xr = x - e.fsum[2], yr = y - e.fsum[3], zr = z - e.fsum[4];
+      const double nx2 = -(xr * xr + yr * yr + zr * zr);
+      for (int b = 0; b < n_hm; b += SRC_TILE) {
+        const int cnt = min(SRC_TILE, n_hm - b);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += EN_T) {
+          sa[k] = e.src_f[b + k];
+          sb[k] = make_double4(e.src_a[b + k].w, e.src_b[b + k].x, 0.0, 0.0);
+        }
+        __syncthreads();
+        if (is_lm) {
+          for (int k0 = 0; k0 < cnt; k0 += 64) {
+            const int gn = min(64, cnt - k0);
+            unsigned long long marked = 0ull;
+#pragma unroll 8
+            for (int kk = 0; kk < gn; kk++) {
+              const double4 F = sa[k0 + kk];
+              const double t = fma(F.x, xr, fma(F.y, yr, fma(F.z, zr, F.w)));
+              if (t < nx2) marked |= 1ull << kk;
+            }
+            while (marked) {
+              const int kk = __ffsll((long long)marked) - 1;
+              marked &= marked - 1ull;
+              l26 += (sb[k0 + kk].x * eta_l) * p.dt_s;
+              l60 += (sb[k0 + kk].y * eta_l) * p.dt_s;
+            }
+          }
+        }
+      }
+    } else if (__syncthreads_or(full_scan ? 1 : 0)) {
+      // mode 2 fallback (rare): exact all-pairs scan for the discs that overflowed their hit list
+      for (int b = 0; b < n_hm; b += SRC_TILE) {
+        const int cnt = min(SRC_TILE, n_hm - b);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += EN_T) {
+          sa[k] = e.src_a[b + k];
+          sb[k] = e.src_b[b + k];
+        }
+        __syncthreads();
+        if (full_scan) {
+          for (int kk = 0; kk < cnt; kk++) {
+            const double4 A = sa[kk];
+            const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (!(d2 >= p.q_local)) {
+              l26 += (A.w * eta_l) * p.dt_s;
+              l60 += (sb[kk].x * eta_l) * p.dt_s;
+            }
+          }
         }
       }
     }
@@ -189,19 +491,19 @@ __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const 
   inv[4] = (inv[4] + l60) * p.decay60;
   inv[5] = (inv[5] + g60) * p.decay60;
   inv[6] = s60 * p.decay60;
-  if (p.with_agb) {
+  if (agb) {
     inv[3] *= p.decay26;
     inv[7] *= p.decay60;
   }
 #pragma unroll
-  for (int r = 0; r < ENR_NINV; r++) e.inv[r * n + li] = inv[r];
+  for (int r = 0; r < ENR_NINV; r++)
+    if (agb || (r != 3 && r != 7)) e.inv[r * n + li] = inv[r];  // the agb rows are untouched without an interloper
   // condense (:1071-1086)
-  if (is_lm && e.alive[li]) {
-    const double tau = e.tau_disk[li];
+  if (is_lm && was_alive) {
     if (tau >= p.t_new_myr) {
 #pragma unroll
       for (int r = 0; r < ENR_NINV; r++)
-        if (p.with_agb || (r != 3 && r != 7)) e.fin[r * n + li] = inv[r];
+        if (agb || (r != 3 && r != 7)) e.fin[r * n + li] = inv[r];
     }
     if (tau < p.t_new_myr) e.alive[li] = 0;
   }
@@ -262,11 +564,40 @@ int launch_interloper(const EnrichDev &e, const InterloperParams &p, cudaStream_
   return 1;
 }
 
-int launch_enrich(const EnrichDev &e, const EnrichParams &p, cudaStream_t s) {
-  k_enrich_classify<<<(e.n_tot + EN_T - 1) / EN_T, EN_T, 0, s>>>(e);
-  k_enrich_sources<<<1, 1024, 0, s>>>(e);
-  k_enrich_discs<<<(e.n_loc + EN_T - 1) / EN_T, EN_T, 0, s>>>(e, p);
-  return 3;
+int enrich_sources_grid(int n_tot, int sm_count) {
+  int g = (n_tot + SRC_T - 1) / SRC_T;
+  const int cap = sm_count > 0 ? 2 * sm_count : 296;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+// classify + sort only (phase 1 of the sliced multi-GPU upload)
+int launch_enrich_classify(const EnrichDev &e, const EnrichParams &p, int sm_count, cudaStream_t s) {
+  k_enrich_sources<<<enrich_sources_grid(e.n_tot, sm_count), SRC_T, 0, s>>>(e, p, 1);
+  return 1;
+}
+
+// tables_only: the source list is already on the device (sorted) and the compact rows e.hm_rows are filled
+int launch_enrich(const EnrichDev &e, const EnrichParams &p, int sm_count, bool tables_only, cudaStream_t s, cudaError_t *err) {
+  if (tables_only) k_enrich_sources<<<1, SRC_T, 0, s>>>(e, p, 2);
+  else k_enrich_sources<<<enrich_sources_grid(e.n_tot, sm_count), SRC_T, 0, s>>>(e, p, 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((e.n_loc + EN_T - 1) / EN_T);
+  cfg.blockDim = dim3(EN_T);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t rc;
+  switch (p.mode) {
+    case 1: rc = cudaLaunchKernelEx(&cfg, k_enrich_discs<1>, e, p); break;
+    case 2: rc = cudaLaunchKernelEx(&cfg, k_enrich_discs<2>, e, p); break;
+    default: rc = cudaLaunchKernelEx(&cfg, k_enrich_discs<0>, e, p); break;
+  }
+  if (err) *err = rc;
+  return 2;
 }
 
 }  // namespace al26

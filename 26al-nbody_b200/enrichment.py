@@ -57,6 +57,12 @@ class EnrichCore:
         fin = None if fin is None else _lib.f64(fin)
         self.ctx.chk(self.L.al26_enrich_set_inventories(self.h, self.n, _lib.ptr(inv), _lib.ptr(fin)))
 
+    def set_mode(self, mode):
+        """0 exact (bit-identical to the reference kernel; default), 1 fast (tolerance 1e-10: hoisted global sum,
+        4-instruction pair test), 2 fast + cell-grid pruning (see include/al26_b200.h)"""
+        mode = {"exact": 0, "fast": 1, "pruned": 2}.get(mode, mode)
+        self.ctx.chk(self.L.al26_enrich_set_mode(self.h, int(mode)))
+
     def set_units(self, km_per_length, kms_per_speed):
         self.ctx.chk(self.L.al26_enrich_set_units(self.h, float(km_per_length), float(kms_per_speed)))
 

@@ -228,6 +228,14 @@ int al26_enrich_set_inventories(al26_ctx *ctx, int64_t n, const double *inv /*[8
  * in place: x_km = x_nbody * km_per_length, v_kms = v_nbody * kms_per_speed
  * (replaces `.value_in(units.km)` / `.value_in(units.km/units.s)`, al26_nbody.py:886-891) */
 int al26_enrich_set_units(al26_ctx *ctx, double km_per_length, double kms_per_speed);
+/* how the disc kernel treats the (disc, massive star) pairs -- no reference counterpart, a knob of this library:
+ *   0 (default) exact: every pair in the reference's order; wind sums bit-identical to the reference's numba kernel;
+ *   1 fast: the north_star's tolerance mode (per-disc masses within 1e-10): the separable global-bubble source sum is
+ *     hoisted (relative difference ~1e-13), the local-bubble test runs in expanded form, 3 DFMA + 1 compare per pair;
+ *     local and SN deposits stay bit-identical unless a pair sits within ~1e-12 (relative) of the bubble surface;
+ *   2 fast + pruned: as 1, with the local-bubble candidates taken from a cell grid over the massive stars and tested
+ *     in the exact form (local rows bit-identical to mode 0); no pair loop, HBM-bound at any source count. */
+int al26_enrich_set_mode(al26_ctx *ctx, int mode);
 /* replaces one pass of al26_nbody.py:878-1086 (interloper block excluded):
  *   classify (:1194-1216) on mass_msun; 4x calc_wind_abs (:642-702, :897-938) with local bubble
  *   r_bub_local_km (distance-tested) and global bubble r_bub_global_km (= virial radius, no

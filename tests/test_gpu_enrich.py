@@ -208,3 +208,82 @@ def test_local_densities_large_sample_vs_oracle(pkg, ctx):
         assert rho[i] == mass / (ao.FTP * d[nr[-1]] * d[nr[-1]] * d[nr[-1]])
     with pytest.raises(pkg.Al26Error):
         ctx.local_densities(x[:5], y[:5], z[:5], m[:5])
+
+
+def _run_modes(pkg, ctx, n, n_hm, seed, steps=6, clustered=False):
+    """the same multi-step problem in the three disc-kernel modes; returns {mode: (inv, fin, alive, kicked, events)}"""
+    out = {}
+    for mode in (0, 1, 2):
+        P = _random_problem(n, n_hm, seed=seed)
+        rng = P["rng"]
+        for s_ in ((2, 4) if n_hm else ()):  # the two stars that die below do have a supernova yield
+            P["sn26"][P["hm"][s_ % n_hm]], P["sn60"][P["hm"][s_ % n_hm]] = 5e25, 5e24
+        e = pkg.EnrichCore(ctx=ctx)
+        e.set_mode(mode)
+        try:
+            e.commit(P["rdisk"], P["tau"], P["alive"], np.zeros(n), P["wr26"], P["wr60"], P["sn26"], P["sn60"])
+            pos = rng.normal(0, 3e13, (3, n)); vel = rng.normal(0, 1.0, (3, n))
+            if clustered:  # every disc within a few bubble radii of the sources: many hits per disc (mode 2's fallback)
+                pos = rng.normal(0, 2e12, (3, n))
+            elif n_hm:
+                pos[:, ::5] = pos[:, P["hm"][0:1]] + rng.normal(0, 1e12, (3, len(pos[0, ::5])))
+            mdot = np.zeros(n); mdot[P["hm"]] = 10.0 ** rng.uniform(14, 17, n_hm)
+            dt_myr, dt_s = 0.01, 0.01 * 1e6 * 365.242199 * 86400
+            f26, f60 = eo.decay_fractions(dt_myr)
+            events = []
+            for step in range(1, steps + 1):
+                if n_hm and step in (2, 4):
+                    mdot[P["hm"][step % n_hm]] = 0.0
+                pos += vel * 1e10
+                events.append(e.step(P["mass"], mdot, np.concatenate([pos, vel]), dt_s, step * dt_myr, 3.0856775814913e12,
+                                     2.1e14, f26, f60).tolist())
+            out[mode] = e.get() + (events,)
+        finally:
+            e.set_mode(0)
+    return out
+
+
+@pytest.mark.parametrize("n,n_hm,clustered", [(4000, 9, False), (6000, 700, False), (3000, 40, True), (500, 0, False)])
+def test_fast_modes_agree_with_the_exact_mode(pkg, ctx, n, n_hm, clustered):
+    """Modes 1 (hoisted global sum, expanded bubble test) and 2 (cell-grid pruning) against mode 0, which is itself
+    bit-exact against the reference kernel: integer work and the local / SN rows identical, the global rows within the
+    north_star's 1e-10 (here: 1e-12, summation order only)."""
+    out = _run_modes(pkg, ctx, n, n_hm, seed=n + n_hm, clustered=clustered)
+    R = pkg.ROW
+    inv0, fin0, alive0, kicked0, ev0 = out[0]
+    if n_hm:
+        assert np.count_nonzero(inv0[R["local26"]]) > 0 and np.count_nonzero(inv0[R["sne26"]]) > 0
+    for mode in (1, 2):
+        inv, fin, alive, kicked, ev = out[mode]
+        assert ev == ev0 and np.array_equal(alive, alive0) and np.array_equal(kicked, kicked0)
+        for row in ("local26", "local60", "sne26", "sne60", "agb26", "agb60"):
+            assert np.array_equal(inv[R[row]], inv0[R[row]]), (mode, row)
+            assert np.array_equal(fin[R[row]], fin0[R[row]]), (mode, row)
+        for row in ("global26", "global60"):
+            for a, b in ((inv, inv0), (fin, fin0)):
+                nz = b[R[row]] != 0
+                assert np.array_equal(a[R[row]] != 0, nz)
+                assert np.max(np.abs(a[R[row]][nz] / b[R[row]][nz] - 1.0), initial=0.0) < 1e-12, (mode, row)
+
+
+def test_capacity_error_leaves_the_state_untouched(pkg, ctx):
+    """more massive stars than the source table holds: AL26_ECAP, and neither inventories nor flags have moved"""
+    n = 20000
+    rng = np.random.default_rng(3)
+    mass = np.full(n, 1.0); mass[:9000] = 20.0
+    wr = np.where(mass > 13, 1e-5, 0.0)
+    pv = np.concatenate([rng.normal(0, 3e13, (3, n)), rng.normal(0, 1.0, (3, n))])
+    e = pkg.EnrichCore(ctx=ctx)
+    e.commit(np.full(n, 1.5e10), np.full(n, 0.015), np.ones(n), np.zeros(n), wr, wr, wr * 1e30, wr * 1e30)
+    ok_mass = mass.copy(); ok_mass[100:9000] = 5.0
+    e.step(ok_mass, np.where(ok_mass > 13, 1e16, 0.0), pv, 3e11, 0.01, 3e12, 3e13, 0.99, 0.999)
+    before = e.get()
+    with pytest.raises(pkg.Al26Error) as ei:
+        e.step(mass, np.zeros(n), pv, 3e11, 0.02, 3e12, 3e13, 0.99, 0.999)  # 9000 sources, every one a supernova
+    assert ei.value.code == -4
+    after = e.get()
+    for a, b in zip(before, after):
+        assert np.array_equal(a, b)
+    # and the context still works
+    ev = e.step(ok_mass, np.zeros(n), pv, 3e11, 0.02, 3e12, 3e13, 0.99, 0.999)
+    assert len(ev) == 100 and e.get()[3][:100].all()
