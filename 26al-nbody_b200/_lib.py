@@ -44,6 +44,7 @@ SIGNATURES = {
     "al26_dist_set_split_min": (C.c_int, [_VP, C.c_int]),
     "al26_dist_p2p_export": (C.c_int, [_VP, _VP]),
     "al26_dist_p2p_import": (C.c_int, [_VP, _VP, C.c_int]),
+    "al26_dist_profile": (C.c_int, [_VP, _PI64]),
     "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
     "al26_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
     "al26_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "al26_grav_loop_profile": (C.c_int, [_VP, _PI64]),
     "al26_bench_fp64_peak": (C.c_int, [_VP, _PD]),
     "al26_bench_fp64_with_rsqrt": (C.c_int, [_VP, _PD]),
+    "al26_bench_fp64_rate": (C.c_int, [_VP, C.c_int, _PD]),
     "al26_local_densities": (C.c_int, [_VP, C.c_int64, _D, _D, _D, _D, _D]),
     "al26_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
@@ -219,6 +221,15 @@ class Context:
         names = ("force_arrive", "wait_partials", "reduce_correct", "-", "wait_release", "fused_total", "scan", "barrier")
         return {k: v for k, v in zip(names, list(h)) if k != "-"}
 
+    def dist_profile(self):
+        """peer-memory mode: CTA 0's SM cycles per step category since the last commit (include/al26_b200.h)"""
+        h = (C.c_int64 * 12)()
+        self.chk(self.L.al26_dist_profile(self.h, h))
+        names = ("fused_cycles", "fused_steps", "redundant_cycles", "redundant_steps", "redundant_active",
+                 "exch_predict_cycles", "exch_force_cycles", "exch_correct_cycles", "exch_barrier_cycles", "exch_steps",
+                 "exch_active", "-")
+        return {k: v for k, v in zip(names, list(h)) if k != "-"}
+
     def block_histogram(self):
         h = (C.c_int64 * 32)()
         self.chk(self.L.al26_grav_block_histogram(self.h, h))
@@ -233,6 +244,12 @@ class Context:
         tf = C.c_double(0)
         self.chk(self.L.al26_bench_fp64_peak(self.h, C.byref(tf)))
         return tf.value
+
+    def fp64_rate(self, variant):
+        """FP64 lane-instructions per second of the operand-pattern microbenchmark `variant` (include/al26_b200.h)"""
+        r = C.c_double(0)
+        self.chk(self.L.al26_bench_fp64_rate(self.h, int(variant), C.byref(r)))
+        return r.value
 
     def fp64_with_rsqrt_tflops(self):
         """DFMA TFLOP/s left when one independent MUFU.RSQ64H rides along per 32 DFMAs (the force kernel's ratio)"""

@@ -23,6 +23,7 @@ struct StepCtrl {
   int pad[4];                      // [0] peer-memory mode: active particles this rank owns; [1] fused steps: slots corrected
 };
 
+constexpr int DIST_PROF_N = 12;
 struct GravHeader {
   double span;  // length of the current evolve call
   double D;     // largest step of the call's dyadic ladder
@@ -43,6 +44,11 @@ struct GravHeader {
   long long n_fused;             // diagnostic: block steps taken through the fused path, since the last commit
   long long n_engine;            // diagnostic: block steps taken by the cluster engine, since the last commit
   long long fuse_ns[16];         // diagnostic (builds with -DAL26_FUSE_TIMING only): globaltimer ns per fused-step segment
+  // peer-memory mode, CTA 0's SM cycles since the last commit: [0] fused redundant steps, [1] their number, [2] other
+  // redundant steps, [3] their number, [4] their active particles; exchanged steps: [5] predictor + scheduler + barrier,
+  // [6] force on the own share + barrier, [7] corrector + peer stores, [8] cross-GPU barrier, [9] their number,
+  // [10] their active particles
+  long long dist_prof[DIST_PROF_N];
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
@@ -233,6 +239,7 @@ int force_variant_count();
 int force_variant_info(int v, int *ctas_per_sm, int *ipt);
 double launch_dfma_peak(int sm_count, int iters, double *scratch, cudaStream_t s);  // returns flops per launch
 double launch_dfma_mufu_mix(int sm_count, int iters, double *scratch, cudaStream_t s);  // + 1 MUFU.RSQ64H per 32 DFMA
+double launch_fp64_rate(int variant, int sm_count, int iters, double *scratch, cudaStream_t s);  // returns DP lane-instructions per launch
 cudaError_t force_kernel_setup();
 int launch_loop(const GravDev &g, int phase, int max_steps, cudaStream_t s, cudaError_t *err);
 int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsigned long long step_id0,
@@ -257,8 +264,9 @@ int energy_grid(int n_loc);
 // enrichment (K5)
 constexpr int ENR_NINV = 8;
 constexpr int ENR_MAX_SOURCES = 8192;
-constexpr int ENR_GRID_MAX = 32;                                           // mode 2: cells per dimension at most
-constexpr int ENR_GRID_CELLS = ENR_GRID_MAX * ENR_GRID_MAX * ENR_GRID_MAX;
+constexpr int ENR_GRID_MAX = 48;                                           // mode 2: cells per dimension at most (plus a one-cell apron)
+constexpr int ENR_GRID_CELLS = (ENR_GRID_MAX + 2) * (ENR_GRID_MAX + 2) * (ENR_GRID_MAX + 2);
+constexpr int ENR_PRUNE_MIN_SOURCES = 48;                                  // mode 2: below this many massive stars every pair is tested
 constexpr int ENR_NCOUNTERS = 16;
 struct EnrichDev {
   int n_tot;      // global star count (classification, source table)
@@ -278,7 +286,7 @@ struct EnrichDev {
   // scratch
   int *hm_list;       // [ENR_MAX_SOURCES] massive stars, ascending index after the sort
   int *counters;      // [0] massive stars found, [1] n_events, [2] capacity flag, [3] n_hm (sorted list), [4] CTAs done,
-                      // [5..7] grid cells per dimension (mode 2)
+                      // [5..7] grid cells per dimension (mode 2), [8] candidate lists built
   double4 *src_a;     // {x, y, z, c26}
   double4 *src_b;     // {c60, sn26, sn60, is_event}
   double4 *src_f;     // fast test: {-2 x', -2 y', -2 z', |s'|^2 - q}, positions relative to fsum[2..4]
@@ -286,8 +294,8 @@ struct EnrichDev {
   double *ev_b;       //                                     sn60
   double *fsum;       // [0] sum c26, [1] sum c60, [2..4] origin of the fast test, [5..7] grid corner, [8] 1 / cell size
   double *hm_rows;    // sliced upload: [mdot, x, y, z][ENR_MAX_SOURCES] of the listed massive stars, gathered by the host
-  int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] starts, then [ENR_GRID_CELLS + 1] scatter cursors
-  int *cell_items;    // [ENR_MAX_SOURCES] source numbers by cell
+  int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] list starts, then [ENR_GRID_CELLS + 1] scatter cursors
+  int *cell_items;    // [27 * ENR_MAX_SOURCES] per-cell candidate lists (every source sits in 27 of them)
   int *sn_events;     // [ENR_MAX_SOURCES]
 };
 struct EnrichParams {

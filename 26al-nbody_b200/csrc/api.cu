@@ -1366,6 +1366,16 @@ int al26_grav_block_histogram(al26_ctx *c, int64_t *hist32) {
   return 0;
 }
 
+int al26_dist_profile(al26_ctx *c, int64_t *out12) {
+  if (!c || !out12) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "dist_profile before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  for (int k = 0; k < DIST_PROF_N; k++) out12[k] = c->h_hdr->dist_prof[k];
+  return 0;
+}
+
 int al26_grav_loop_profile(al26_ctx *c, int64_t *cycles6) {
   if (!c || !cycles6) return AL26_EINVAL;
   if (!c->committed) return fail(c, AL26_ESTATE, "loop_profile before commit");
@@ -1396,6 +1406,29 @@ static int bench_fp64(al26_ctx *c, double *tflops, bool with_mufu) {
   }
   CU(cudaGetLastError());
   *tflops = best;
+  return 0;
+}
+
+int al26_bench_fp64_rate(al26_ctx *c, int variant, double *lane_inst_per_s) {
+  if (!c || !lane_inst_per_s || variant < 0 || variant > 5) return AL26_EINVAL;
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_scratch(c, 1024);
+  if (rc) return rc;
+  launch_fp64_rate(variant, c->sm_count, 2000, c->scratch, c->stream);  // warm-up
+  double best = 0.0;
+  for (int r = 0; r < 5; r++) {
+    CU(cudaEventRecord(c->ev0, c->stream));
+    const double inst = launch_fp64_rate(variant, c->sm_count, 20000, c->scratch, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double rate = inst / (ms * 1e-3);
+    if (rate > best) best = rate;
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  *lane_inst_per_s = best;
   return 0;
 }
 
@@ -1444,7 +1477,7 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   CU(cudaMalloc(&c->e_glob, 12 * nt * sizeof(double)));
   CU(cudaMalloc(&c->e_loc, 20 * nl * sizeof(double)));  // r_disk, tau, inv[8], fin[8], agb_raw[2]
   CU(cudaMalloc(&c->e_flags, nt + nl));
-  const size_t n_ints = ENR_NCOUNTERS + 3 * (size_t)ENR_MAX_SOURCES + 2 * ((size_t)ENR_GRID_CELLS + 1);
+  const size_t n_ints = ENR_NCOUNTERS + 29 * (size_t)ENR_MAX_SOURCES + 2 * ((size_t)ENR_GRID_CELLS + 1);
   CU(cudaMalloc(&c->e_ints, n_ints * sizeof(int)));
   CU(cudaMemsetAsync(c->e_ints, 0, n_ints * sizeof(int), c->stream));
   CU(cudaMalloc(&c->e_src, 4 * ENR_MAX_SOURCES * sizeof(double4)));
@@ -1463,7 +1496,7 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   e.hm_list = c->e_ints + ENR_NCOUNTERS;
   e.sn_events = e.hm_list + ENR_MAX_SOURCES;
   e.cell_items = e.sn_events + ENR_MAX_SOURCES;
-  e.cell_start = e.cell_items + ENR_MAX_SOURCES;
+  e.cell_start = e.cell_items + 27 * ENR_MAX_SOURCES;
   e.src_a = c->e_src; e.src_b = c->e_src + ENR_MAX_SOURCES; e.src_f = c->e_src + 2 * ENR_MAX_SOURCES;
   e.ev_a = c->e_src + 3 * ENR_MAX_SOURCES;
   e.ev_b = c->e_dbl; e.fsum = c->e_dbl + ENR_MAX_SOURCES; e.hm_rows = c->e_dbl + ENR_MAX_SOURCES + 16;

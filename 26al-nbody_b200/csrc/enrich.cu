@@ -26,8 +26,9 @@
 //             test runs on |x|^2 - 2 s.x + (|s|^2 - q) < 0 with the source part precomputed: 3 DFMA + 1 DSETP per
 //             pair.  Local deposits (same terms, same ascending order) and SN deposits (exact difference form over
 //             the event list) stay bit-identical unless a pair sits within ~1e-12 (relative) of the bubble surface.
-//   2 pruned  as 1, but the local-bubble candidates come from a uniform cell grid over the sources (cell >= bubble
-//             radius, <= 32^3 cells, 27-cell neighbourhood) and are tested in the exact difference form: local rows
+//   2 pruned  as 1, but from ENR_PRUNE_MIN_SOURCES massive stars up the local-bubble candidates come from per-cell
+//             lists (uniform grid over the sources, cell >= bubble radius, every source entered into its 27
+//             neighbouring cells: one lookup per disc) and are tested in the exact difference form: local rows
 //             bit-identical to mode 0, the pair loop is gone, the kernel is HBM-bound at any source count.
 #include "al26_internal.cuh"
 
@@ -214,76 +215,82 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
     e.fsum[0] = s26; e.fsum[1] = s60;
     e.fsum[2] = ox; e.fsum[3] = oy; e.fsum[4] = oz;
   }
-  if (p.mode != 2) return;
+  if (p.mode != 2 || n_hm < ENR_PRUNE_MIN_SOURCES) return;  // few sources: the disc kernel scans them all (counters[8] stays 0)
 
-  // ---- mode 2: uniform cell grid over the sources' bounding box; cell size >= the local bubble radius ----
+  // ---- mode 2: per-cell candidate lists.  A uniform grid over the sources' bounding box plus a one-cell apron, cell
+  // size h >= the local bubble radius; every source is entered into the lists of its 27 neighbouring cells, so a
+  // disc needs ONE lookup -- the list of its own cell holds every source that can be within R of it. ----
   for (int c = 0; c < 3; c++) {
     lo[c] = block_min_all(lo[c], shd);
     hi[c] = -block_min_all(-hi[c], shd);
   }
-  int gd[3] = {1, 1, 1};
+  int gd[3];
   double h = p.r_local * (1.0 + 1e-6);
-  if (n_hm > 0) {
+  {
     const double ext = fmax(hi[0] - lo[0], fmax(hi[1] - lo[1], hi[2] - lo[2]));
     h = fmax(h, ext / (double)ENR_GRID_MAX * (1.0 + 1e-9));
     for (int c = 0; c < 3; c++) {
       int g = (int)floor((hi[c] - lo[c]) / h) + 1;
-      gd[c] = g < 1 ? 1 : (g > ENR_GRID_MAX ? ENR_GRID_MAX : g);
+      g = g < 1 ? 1 : (g > ENR_GRID_MAX ? ENR_GRID_MAX : g);
+      gd[c] = g + 2;         // apron
+      lo[c] -= h;
     }
-  } else {
-    lo[0] = lo[1] = lo[2] = 0.0;
   }
   const double inv_h = 1.0 / h;
   const int ncell = gd[0] * gd[1] * gd[2];
   int *start = e.cell_start, *cursor = e.cell_start + (ENR_GRID_CELLS + 1);
   for (int c = tid; c <= ncell; c += SRC_T) start[c] = 0;
   __syncthreads();
-  for (int k = tid; k < n_hm; k += SRC_T) {
-    const double4 A = e.src_a[k];
-    int cx = (int)floor((A.x - lo[0]) * inv_h), cy = (int)floor((A.y - lo[1]) * inv_h), cz = (int)floor((A.z - lo[2]) * inv_h);
-    cx = min(max(cx, 0), gd[0] - 1); cy = min(max(cy, 0), gd[1] - 1); cz = min(max(cz, 0), gd[2] - 1);
-    atomicAdd(&start[(cz * gd[1] + cy) * gd[0] + cx + 1], 1);  // counts shifted by one: the scan leaves starts
-  }
-  __syncthreads();
-  {  // inclusive scan of start[1..ncell] in place (each thread a contiguous run, then the block's run totals)
-    const int per = (ncell + SRC_T - 1) / SRC_T;
-    const int b = 1 + tid * per, en = min(ncell + 1, b + per);
-    int run = 0;
-    for (int c = b; c < en; c++) run += start[c];
-    const int lane = tid & 31, warp = tid >> 5;
-    int incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = tid; k < n_hm; k += SRC_T) {
+      const double4 A = e.src_a[k];
+      int cx = (int)floor((A.x - lo[0]) * inv_h), cy = (int)floor((A.y - lo[1]) * inv_h), cz = (int)floor((A.z - lo[2]) * inv_h);
+      cx = min(max(cx, 1), gd[0] - 2); cy = min(max(cy, 1), gd[1] - 2); cz = min(max(cz, 1), gd[2] - 2);
+      for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+          for (int dx = -1; dx <= 1; dx++) {
+            const int cell = ((cz + dz) * gd[1] + (cy + dy)) * gd[0] + (cx + dx);
+            if (pass == 0) atomicAdd(&start[cell + 1], 1);  // counts shifted by one: the scan leaves the starts
+            else e.cell_items[atomicAdd(&cursor[cell], 1)] = k;
+          }
     }
-    if (lane == 31) shi[warp] = incl;
     __syncthreads();
-    int off = incl - run;
-    for (int w = 0; w < warp; w++) off += shi[w];
-    for (int c = b; c < en; c++) {
-      off += start[c];
-      start[c] = off;
+    if (pass == 1) break;
+    {  // inclusive scan of start[1..ncell] in place (each thread a contiguous run, then the block's run totals)
+      const int per = (ncell + SRC_T - 1) / SRC_T;
+      const int b = 1 + tid * per, en = min(ncell + 1, b + per);
+      int run = 0;
+      for (int c = b; c < en; c++) run += __ldcg(&start[c]);
+      const int lane = tid & 31, warp = tid >> 5;
+      int incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) shi[warp] = incl;
+      __syncthreads();
+      int off = incl - run;
+      for (int w = 0; w < warp; w++) off += shi[w];
+      for (int c = b; c < en; c++) {
+        off += __ldcg(&start[c]);
+        start[c] = off;
+      }
     }
-  }
-  __syncthreads();
-  for (int c = tid; c < ncell; c += SRC_T) cursor[c] = start[c];
-  __syncthreads();
-  for (int k = tid; k < n_hm; k += SRC_T) {
-    const double4 A = e.src_a[k];
-    int cx = (int)floor((A.x - lo[0]) * inv_h), cy = (int)floor((A.y - lo[1]) * inv_h), cz = (int)floor((A.z - lo[2]) * inv_h);
-    cx = min(max(cx, 0), gd[0] - 1); cy = min(max(cy, 0), gd[1] - 1); cz = min(max(cz, 0), gd[2] - 1);
-    e.cell_items[atomicAdd(&cursor[(cz * gd[1] + cy) * gd[0] + cx], 1)] = k;
+    __syncthreads();
+    for (int c = tid; c < ncell; c += SRC_T) cursor[c] = __ldcg(&start[c]);
+    __syncthreads();
   }
   if (tid == 0) {
     e.counters[5] = gd[0]; e.counters[6] = gd[1]; e.counters[7] = gd[2];
+    e.counters[8] = 1;  // the lists are there
     e.fsum[5] = lo[0]; e.fsum[6] = lo[1]; e.fsum[7] = lo[2]; e.fsum[8] = inv_h;
   }
 }
 
 // one thread per star.  MODE: see the file header.
 template <int MODE>
-__global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const EnrichParams p) {
+__global__ void __launch_bounds__(EN_T, 4) k_enrich_discs(const EnrichDev e, const EnrichParams p) {
   __shared__ double4 sa[SRC_TILE];
   __shared__ double4 sb[SRC_TILE];
   const int li = blockIdx.x * EN_T + threadIdx.x;
@@ -382,53 +389,48 @@ __global__ void __launch_bounds__(EN_T) k_enrich_discs(const EnrichDev e, const 
         s60 += e.ev_b[q] * eta;
       }
     }
-    bool full_scan = (MODE == 1);
-    if (MODE == 2 && is_lm && n_hm > 0) {
-      const int gx = e.counters[5], gy = e.counters[6], gz = e.counters[7];
+    const bool have_lists = (MODE == 2) && __ldcg(&e.counters[8]) != 0;  // uniform; few sources -> the all-pairs loop below
+    bool full_scan = false;
+    if (have_lists && is_lm) {
+      const int gx = __ldcg(&e.counters[5]), gy = __ldcg(&e.counters[6]), gz = __ldcg(&e.counters[7]);
       const double inv_h = e.fsum[8];
-      const double ux = fmin(fmax((x - e.fsum[5]) * inv_h, -4.0), 64.0), uy = fmin(fmax((y - e.fsum[6]) * inv_h, -4.0), 64.0),
-                   uz = fmin(fmax((z - e.fsum[7]) * inv_h, -4.0), 64.0);
-      const int cx = (int)floor(ux), cy = (int)floor(uy), cz = (int)floor(uz);
-      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gx - 1);
-      int hits[MATCH_CAP];
-      int nh = 0;
-      if (x0 <= x1) {
-        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, gz - 1); zz++) {
-          for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); yy++) {
-            const int row = (zz * gy + yy) * gx;
-            const int tb = __ldg(&e.cell_start[row + x0]), te = __ldg(&e.cell_start[row + x1 + 1]);
-            for (int t = tb; t < te; t++) {
-              const int k = __ldg(&e.cell_items[t]);
-              const double4 A = e.src_a[k];
-              const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
-              const double d2 = dx * dx + dy * dy + dz * dz;
-              if (!(d2 >= p.q_local)) {
-                if (nh < MATCH_CAP) hits[nh] = k;
-                nh++;
-              }
+      const double ux = (x - e.fsum[5]) * inv_h, uy = (y - e.fsum[6]) * inv_h, uz = (z - e.fsum[7]) * inv_h;
+      // outside the grid (apron included) no source can be within R; the comparisons also drop NaNs
+      if (ux >= 0.0 && uy >= 0.0 && uz >= 0.0 && ux < (double)gx && uy < (double)gy && uz < (double)gz) {
+        const int cell = ((int)uz * gy + (int)uy) * gx + (int)ux;
+        const int tb = __ldg(&e.cell_start[cell]), te = __ldg(&e.cell_start[cell + 1]);
+        int hits[MATCH_CAP];
+        int nh = 0;
+        for (int t = tb; t < te; t++) {
+          const int k = __ldg(&e.cell_items[t]);
+          const double4 A = e.src_a[k];
+          const double dx = x - A.x, dy = y - A.y, dz = z - A.z;
+          const double d2 = dx * dx + dy * dy + dz * dz;
+          if (!(d2 >= p.q_local)) {
+            if (nh < MATCH_CAP) hits[nh] = k;
+            nh++;
+          }
+        }
+        if (nh > MATCH_CAP) {
+          full_scan = true;  // a disc inside more bubbles than the hit list holds: take the all-pairs scan for it
+        } else {
+          for (int a = 1; a < nh; a++) {  // ascending source order = the reference's summation order
+            const int v = hits[a];
+            int b = a - 1;
+            while (b >= 0 && hits[b] > v) {
+              hits[b + 1] = hits[b];
+              b--;
             }
+            hits[b + 1] = v;
           }
-        }
-      }
-      if (nh > MATCH_CAP) {
-        full_scan = true;  // a disc inside more bubbles than the hit list holds: take the all-pairs scan for it
-      } else {
-        for (int a = 1; a < nh; a++) {  // ascending source order = the reference's summation order
-          const int v = hits[a];
-          int b = a - 1;
-          while (b >= 0 && hits[b] > v) {
-            hits[b + 1] = hits[b];
-            b--;
+          for (int a = 0; a < nh; a++) {
+            l26 += (e.src_a[hits[a]].w * eta_l) * p.dt_s;
+            l60 += (e.src_b[hits[a]].x * eta_l) * p.dt_s;
           }
-          hits[b + 1] = v;
-        }
-        for (int a = 0; a < nh; a++) {
-          l26 += (e.src_a[hits[a]].w * eta_l) * p.dt_s;
-          l60 += (e.src_b[hits[a]].x * eta_l) * p.dt_s;
         }
       }
     }
-    if (MODE == 1) {
+    if (MODE == 1 || !have_lists) {
       // all pairs, 3 DFMA + 1 DSETP each: d^2 - q = |x'|^2 + (-2 s'.x' + |s'|^2 - q), positions relative to the origin
       const double xr = x - e.fsum[2], yr = y - e.fsum[3], zr = z - e.fsum[4];
       const double nx2 = -(xr * xr + yr * yr + zr * zr);

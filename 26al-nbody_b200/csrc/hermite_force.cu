@@ -95,6 +95,52 @@ __global__ void __launch_bounds__(512, 2) k_dfma_mufu_mix(double *out, int iters
   if (r == 123.456) out[0] = r;  // never true; keeps the chains alive
 }
 
+// Operand-pattern variants of the FP64 issue-rate microbenchmark (8 independent chains per thread, 512 threads x 2 CTAs
+// per SM): what limits a DFMA with three distinct register operands -- the pipe or the register file?
+//   1: x = fma(x, imm, b)   two register reads per instruction    2: x = x + b (DADD)    3: x = x * imm (DMUL)
+//   4: x = fma(x, x, b)     5: x = fma(x, a_k, b_k) with per-chain a_k, b_k (three distinct registers, no sharing)
+template <int V>
+__global__ void __launch_bounds__(512, 2) k_fp64_rate(double *out, int iters, double a, double b) {
+  double x[8], ak[8], bk[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    x[k] = (double)threadIdx.x + k;
+    ak[k] = a + 1e-9 * k;
+    bk[k] = b * (k + 1);
+  }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (V == 1) x[k] = fma(x[k], 0.99951171875, b);
+        else if (V == 2) x[k] = x[k] + b;
+        else if (V == 3) x[k] = x[k] * 0.99951171875;
+        else if (V == 4) x[k] = fma(x[k], x[k], b);
+        else x[k] = fma(x[k], ak[k], bk[k]);
+      }
+    }
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r += x[k];
+  if (r == 123.456) out[0] = r;  // never true; keeps the chains alive
+}
+
+// returns DP lane-instructions per launch
+double launch_fp64_rate(int variant, int sm_count, int iters, double *scratch, cudaStream_t s) {
+  const int blocks = sm_count * 2, threads = 512;
+  switch (variant) {
+    case 1: k_fp64_rate<1><<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+    case 2: k_fp64_rate<2><<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+    case 3: k_fp64_rate<3><<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+    case 4: k_fp64_rate<4><<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+    case 5: k_fp64_rate<5><<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+    default: k_dfma_peak<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9); break;
+  }
+  return (double)blocks * threads * 64.0 * (double)iters;
+}
+
 double launch_dfma_mufu_mix(int sm_count, int iters, double *scratch, cudaStream_t s) {
   const int blocks = sm_count * 2, threads = 512;
   k_dfma_mufu_mix<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9);
@@ -128,6 +174,7 @@ __global__ void __launch_bounds__(EN_THREADS) k_energy_pairs(const EnergyDev e, 
   double u = 0.0, s = 0.0;
   const double eps2 = e.eps2;
   const bool soft = eps2 != 0.0;
+  const int self = valid ? e.i0 + i : -1;
   for (int b = j0; b < j1; b += EN_TJ) {
     const int cnt = min(EN_TJ, j1 - b);
     __syncthreads();
@@ -140,7 +187,8 @@ __global__ void __launch_bounds__(EN_THREADS) k_energy_pairs(const EnergyDev e, 
       const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
       const double ri = rsqrt_masked(r2);
       s = fma(pj.w, ri, s);
-      if (soft) u = fma(pj.w, rsqrt_masked(r2 + eps2), u);
+      // softened sum: the self pair (not dropped by the masked rsqrt: r^2 + eps2 > 0) is taken out by index
+      if (soft) u = fma((b + k == self) ? 0.0 : pj.w, rsqrt_masked(r2 + eps2), u);
     }
   }
   if (!soft) u = s;

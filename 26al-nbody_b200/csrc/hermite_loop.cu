@@ -422,8 +422,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   __shared__ unsigned long long sh[C::THREADS / 32];
   __shared__ double shr[C::THREADS / 32][7];
   __shared__ unsigned long long sh_tmin;
+  // time split of the call as CTA 0 sees it (al26_dist_profile): stamps and accumulators live in shared memory, so
+  // the instrumentation holds no registers across the force loop; flushed to the header once, at the end
+  __shared__ long long tp_stamp[5];
+  __shared__ long long tp_acc[DIST_PROF_N];
   const unsigned n_ctas = gridDim.x;
   const bool first = (blockIdx.x == 0 && threadIdx.x == 0);
+  if (first)
+    for (int k = 0; k < DIST_PROF_N; k++) tp_acc[k] = 0;
+#define TP_STAMP(k) if (first) tp_stamp[k] = clock64()
+#define TP_ADD(k, a, b) tp_acc[k] += tp_stamp[b] - tp_stamp[a]
   force_smem_init<C>(sm);
   uint32_t it = 0;
   unsigned target = 0;
@@ -457,9 +465,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     } else {
       tn = span;
     }
+    TP_STAMP(0);
     if (fuse) phase_scan_chunk<true>(g, cur, nxt, tn, CHUNK_J0, CHUNK_CNT, &sm.pos[0][0], &sm.vel[0][0], sh, prev_exch ? xid : 0ull);
     else phase_predict_list<MODE, true>(g, cur, nxt, tn, blockIdx.x, n_ctas, sh, prev_exch ? xid : 0ull);
     if (!grid_barrier(g.hdr, target, n_ctas)) break;
+    TP_STAMP(1);
     if (first) {  // after the barrier: nobody polls the previous step's counters any more (see k_loop)
       old->t_next_bits = INF_BITS;
       old->n_act = 0;
@@ -474,6 +484,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
       // ---- redundant AND small: the fused path (one barrier, see above) ----
       if (!fused_step<C>(g, sm, cur, nxt, n_all, CHUNK_CNT, CHUNK_PARTS, tn, g.Dmax, shr, &sh_tmin, n_own, tnext_bits)) break;
       prev_exch = false;
+      TP_STAMP(2);
+      if (first) {
+        TP_ADD(0, 0, 2);
+        tp_acc[1] += 1;
+      }
     } else if (!exchange) {
       // ---- redundant step: all active particles, local stores, local barrier ----
       if (n_all > 0) force_items<C>(g, sm, cur, n_all, n_ctas, it);
@@ -482,16 +497,33 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
       if (!grid_barrier(g.hdr, target, n_ctas)) break;
       tnext_bits = __ldcg(&nxt->t_next_bits);
       prev_exch = false;
+      TP_STAMP(2);
+      if (first) {
+        TP_ADD(2, 0, 2);
+        tp_acc[3] += 1;
+        tp_acc[4] += n_all;
+      }
     } else {
       // ---- exchanged step: own share, peer stores, cross-GPU barrier ----
       const unsigned long long this_id = xid + 1;
       if (n_own > 0) force_items<C>(gown, sm, cur, n_own, n_ctas, it);
       if (!grid_barrier(g.hdr, target, n_ctas)) break;
+      TP_STAMP(2);
       if (n_own > 0) phase_correct<MODE, true>(gown, nxt, n_own, tn, blockIdx.x, n_ctas, sh, shr, this_id);
       const bool did_store = n_own > 0 && (int)blockIdx.x < n_own;  // superset of the CTAs that corrected a slot
+      TP_STAMP(3);
       if (!dist_barrier(g, target, n_ctas, this_id, nxt, did_store, &sh_tmin, tnext_bits)) break;
       xid = this_id;
       prev_exch = true;
+      TP_STAMP(4);
+      if (first && MODE == MODE_STEP) {
+        TP_ADD(5, 0, 1);   // predictor + scheduler + barrier
+        TP_ADD(6, 1, 2);   // force on the own share + barrier
+        TP_ADD(7, 2, 3);   // corrector + peer stores
+        TP_ADD(8, 3, 4);   // cross-GPU barrier
+        tp_acc[9] += 1;
+        tp_acc[10] += n_all;
+      }
     }
     ph = (ph + 1) % 3;
     if (first) g.ctrl[ph].t_next_bits = tnext_bits;  // the next block time, for the host / the next launch
@@ -501,7 +533,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     g.hdr->dist_step = xid;
     g.hdr->dist_tnext_bits = tnext_bits;
     g.hdr->dist_prev_exch = (MODE == MODE_STEP && prev_exch) ? 1 : 0;  // init / sync steps are pulled by k_pull
+    for (int k = 0; k < DIST_PROF_N; k++) g.hdr->dist_prof[k] += tp_acc[k];
   }
+#undef TP_STAMP
+#undef TP_ADD
 }
 
 // pull the records staged during block step `step_id` into the local state (after an init / sync step)

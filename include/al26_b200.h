@@ -76,6 +76,12 @@ int al26_dist_set_split_min(al26_ctx *ctx, int n_act_min);
 int al26_dist_p2p_export(al26_ctx *ctx, void *out64);
 int al26_dist_p2p_import(al26_ctx *ctx, const void *handles, int world);
 
+/* diagnostic, peer-memory mode: where a rank's time goes, in SM cycles of CTA 0 since the last commit (12 values):
+ * [0] fused redundant steps, [1] their number, [2] other redundant steps, [3] their number, [4] their active
+ * particles; exchanged steps: [5] predictor + scheduler + barrier, [6] force on the own share + barrier,
+ * [7] corrector + peer stores, [8] cross-GPU barrier, [9] their number, [10] their active particles */
+int al26_dist_profile(al26_ctx *ctx, int64_t *cycles12);
+
 /* ---- gravity -------------------------------------------------------------------------*/
 /* replaces: `gravity.parameters.epsilon_squared / timestep_parameter` (never set by the
  * script; defaults eps2 = 0, eta = 0.14).  dt_max / dt_min are rounded down to powers of 2. */
@@ -203,6 +209,10 @@ int al26_grav_loop_profile(al26_ctx *ctx, int64_t *cycles6);
 /* bench hook: measured FP64 FMA throughput (TFLOP/s) of a DFMA-only microkernel on this GPU:
  * the roofline denominator of the force kernel */
 int al26_bench_fp64_peak(al26_ctx *ctx, double *tflops);
+/* the FP64 issue rate (lane-instructions per second; nominal 148 SMs x 64 lanes x clock) by operand pattern:
+ * 0 x=fma(x,a,b) with a, b shared by the chains (the roofline denominator above); 1 x=fma(x,imm,b); 2 x=x+b (DADD);
+ * 3 x=x*imm (DMUL); 4 x=fma(x,x,b); 5 x=fma(x,a_k,b_k), three distinct registers per instruction */
+int al26_bench_fp64_rate(al26_ctx *ctx, int variant, double *lane_inst_per_s);
 /* the same DFMA chains with one independent MUFU.RSQ64H per 32 DFMAs (the force kernel's ratio): the DFMA TFLOP/s
  * that remain -- i.e. whether the 64-bit reciprocal square root takes FP64 issue slots */
 int al26_bench_fp64_with_rsqrt(al26_ctx *ctx, double *tflops);
