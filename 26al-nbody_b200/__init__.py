@@ -7,7 +7,7 @@ The directory name is not a Python identifier; import it with
 Hand-written CUDA lives in csrc/ behind the C-ABI of include/al26_b200.h; there is no CPU fallback.
 """
 from . import units  # noqa: F401
-from ._lib import Al26Error, Context, SO_PATH, HEADER_PATH, dist_unique_id, load  # noqa: F401
+from ._lib import Al26Error, Context, Group, SO_PATH, HEADER_PATH, device_count, dist_unique_id, load  # noqa: F401
 from .particles import Particles, Channel  # noqa: F401
 from .gravity import GravityCore, B200Gravity  # noqa: F401
 from .enrichment import EnrichCore, decay_fractions, NINV, ROWS, ROW  # noqa: F401
@@ -17,5 +17,5 @@ from . import stellar, driver  # noqa: F401
 from .stellar import StellarStub, YieldTables  # noqa: F401
 from .yields_io import Yields  # noqa: F401
 
-__all__ = ["units", "Al26Error", "Context", "Particles", "Channel", "GravityCore", "B200Gravity",
+__all__ = ["units", "Al26Error", "Context", "Group", "device_count", "Particles", "Channel", "GravityCore", "B200Gravity",
            "EnrichCore", "decay_fractions", "ic", "load", "dist_unique_id"]

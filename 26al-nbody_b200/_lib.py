@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libal26b200.so")
+SO_PATH = os.environ.get("AL26_LIB") or os.path.join(_HERE, "csrc", "libal26b200.so")  # AL26_LIB: an instrumented build (csrc/build.py)
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "al26_b200.h"))
 
 _D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -37,6 +37,7 @@ SIGNATURES = {
     "al26_destroy": (None, [_VP]),
     "al26_last_error": (C.c_char_p, [_VP]),
     "al26_version": (C.c_int, []),
+    "al26_device_count": (C.c_int, []),
     "al26_device_info": (C.c_int, [_VP, _PINT, _PINT, _PI64, _PI64]),
     "al26_dist_unique_id": (C.c_int, [_VP]),
     "al26_dist_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
@@ -45,6 +46,30 @@ SIGNATURES = {
     "al26_dist_p2p_export": (C.c_int, [_VP, _VP]),
     "al26_dist_p2p_import": (C.c_int, [_VP, _VP, C.c_int]),
     "al26_dist_profile": (C.c_int, [_VP, _PI64]),
+    "al26_dist_init_local": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "al26_dist_p2p_local_slab": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
+    "al26_dist_p2p_attach": (C.c_int, [_VP, C.POINTER(C.c_void_p), _PINT, C.c_int]),
+    "al26_group_create": (_VP, [C.c_int, _PINT]),
+    "al26_group_destroy": (None, [_VP]),
+    "al26_group_last_error": (C.c_char_p, [_VP]),
+    "al26_group_size": (C.c_int, [_VP]),
+    "al26_group_ctx": (_VP, [_VP, C.c_int]),
+    "al26_group_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "al26_group_grav_set_reinit_policy": (C.c_int, [_VP, C.c_int]),
+    "al26_group_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
+    "al26_group_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
+    "al26_group_grav_set_time": (C.c_int, [_VP, C.c_double]),
+    "al26_group_grav_get_time": (C.c_int, [_VP, _PD]),
+    "al26_group_grav_evolve": (C.c_int, [_VP, C.c_double, _PI64, _PI64]),
+    "al26_group_grav_get_state": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
+    "al26_group_grav_energies": (C.c_int, [_VP, _PD, _PD, _PD]),
+    "al26_group_last_device_ms": (C.c_int, [_VP, _PD, _PI64]),
+    "al26_group_enrich_commit": (C.c_int, [_VP, C.c_int64, _D, _D, _U8, _U8, _D, _D, _D, _D]),
+    "al26_group_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
+    "al26_group_enrich_set_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_group_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
+    "al26_group_enrich_step": (C.c_int, [_VP, C.c_int64, _D, _D, _VP] + [C.c_double] * 6 + [C.c_int, _I32, C.c_int64, _PI64]),
+    "al26_group_enrich_get": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "al26_grav_set_params": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double]),
     "al26_grav_commit": (C.c_int, [_VP, C.c_int64] + [_D] * 7),
     "al26_grav_set_mass": (C.c_int, [_VP, C.c_int64, _D]),
@@ -113,6 +138,10 @@ def load():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def device_count():
+    return int(load().al26_device_count())
 
 
 def check(ctx, rc):
@@ -268,6 +297,74 @@ class Context:
         ms, nl = C.c_double(0), C.c_int64(0)
         self.chk(self.L.al26_last_device_ms(self.h, C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
+
+
+class _GroupRank:
+    """One rank's context inside a Group, for the per-context tuning hooks and diagnostics (not owned)."""
+
+    def __init__(self, L, h):
+        self.L, self.h = L, C.c_void_p(h)
+
+    def chk(self, rc):
+        check(self.h, rc)
+
+    set_fuse_max = Context.set_fuse_max
+    set_step_mode = Context.set_step_mode
+    dist_profile = Context.dist_profile
+    block_histogram = Context.block_histogram
+    fused_steps = Context.fused_steps
+    device_info = Context.device_info
+
+
+class Group:
+    """Owns one al26_group: n GPUs driven from THIS process, one host thread per GPU inside the library -- the
+    counterpart of `number_of_workers=n` behind the reference's single worker object (al26_nbody.py:57,1711-1720).
+    Same method names as Context where they make sense; `h` is the group handle, `calls` the group entry points."""
+
+    def __init__(self, n_gpus, device_ids=None):
+        self.L = load()
+        ids = None if device_ids is None else (C.c_int * int(n_gpus))(*[int(d) for d in device_ids])
+        h = self.L.al26_group_create(int(n_gpus), ids)
+        if not h:
+            msg = self.L.al26_group_last_error(None)
+            raise Al26Error(-7, (msg.decode() if msg else "al26_group_create failed") + " -- the B200 path has no CPU fallback")
+        self.h = C.c_void_p(h)
+        self.n_gpus = int(n_gpus)
+        self.rank, self.world = 0, 1  # the group is one logical worker: no per-process rank
+
+    def chk(self, rc):
+        if rc != 0:
+            msg = self.L.al26_group_last_error(self.h)
+            raise Al26Error(rc, msg.decode() if msg else "")
+
+    def rank_ctx(self, r):
+        h = self.L.al26_group_ctx(self.h, int(r))
+        if not h:
+            raise Al26Error(-1, f"rank {r} out of range")
+        return _GroupRank(self.L, h)
+
+    def set_fuse_max(self, n_act_max):
+        for r in range(self.n_gpus):
+            self.rank_ctx(r).set_fuse_max(n_act_max)
+
+    def p2p_connect(self):
+        pass  # the library wires the peers' slabs itself (al26_group_grav_commit)
+
+    def last_device_ms(self):
+        ms, nl = C.c_double(0), C.c_int64(0)
+        self.chk(self.L.al26_group_last_device_ms(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.al26_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decomposition(n_act, n_tot, sm_count=148, variant=0, big_nact=2048):

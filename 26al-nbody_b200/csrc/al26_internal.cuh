@@ -264,7 +264,7 @@ int energy_grid(int n_loc);
 // enrichment (K5)
 constexpr int ENR_NINV = 8;
 constexpr int ENR_MAX_SOURCES = 8192;
-constexpr int ENR_GRID_MAX = 48;                                           // mode 2: cells per dimension at most (plus a one-cell apron)
+constexpr int ENR_GRID_MAX = 32;                                           // mode 2: cells per dimension at most (plus a one-cell apron)
 constexpr int ENR_GRID_CELLS = (ENR_GRID_MAX + 2) * (ENR_GRID_MAX + 2) * (ENR_GRID_MAX + 2);
 constexpr int ENR_PRUNE_MIN_SOURCES = 48;                                  // mode 2: below this many massive stars every pair is tested
 constexpr int ENR_NCOUNTERS = 16;
@@ -294,7 +294,7 @@ struct EnrichDev {
   double *ev_b;       //                                     sn60
   double *fsum;       // [0] sum c26, [1] sum c60, [2..4] origin of the fast test, [5..7] grid corner, [8] 1 / cell size
   double *hm_rows;    // sliced upload: [mdot, x, y, z][ENR_MAX_SOURCES] of the listed massive stars, gathered by the host
-  int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] list starts, then [ENR_GRID_CELLS + 1] scatter cursors
+  int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] list starts
   int *cell_items;    // [27 * ENR_MAX_SOURCES] per-cell candidate lists (every source sits in 27 of them)
   int *sn_events;     // [ENR_MAX_SOURCES]
 };
@@ -308,6 +308,7 @@ struct EnrichParams {
 };
 int launch_enrich(const EnrichDev &e, const EnrichParams &p, int sm_count, bool tables_only, cudaStream_t s, cudaError_t *err);
 int launch_enrich_classify(const EnrichDev &e, const EnrichParams &p, int sm_count, cudaStream_t s);
+cudaError_t enrich_kernel_setup();
 
 // AGB interloper deposit (al26_nbody.py:985-1028, calc_intersection :1156-1190)
 struct InterloperParams {

@@ -6,7 +6,11 @@
 #include <nccl.h>  // types only; every NCCL symbol is resolved with dlsym
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -82,6 +86,8 @@ struct al26_ctx {
   int dist_mode = 1;             // world > 1: 1 = peer-memory (NVLink) exchange inside the loop kernel, 0 = NCCL graph path
   void *slab = nullptr;          // own staging slab (peer-memory mode)
   bool p2p_ready = false;        // peers' slabs imported
+  bool p2p_ipc = false;          // ... as CUDA IPC mappings (one process per GPU); false: plain peer pointers (al26_group, one process)
+  bool local_group = false;      // joined by al26_dist_init_local: no NCCL communicator, energies return this rank's partial sums
   unsigned long long dist_step = 0;
   int split_min = 0;             // peer-memory mode: exchange only block steps with at least this many active particles (0 = auto)
 
@@ -263,7 +269,7 @@ void free_gravity(al26_ctx *c) {
   c->graph = nullptr;
   GravDev &g = c->g;
   for (int q = 0; q < MAX_PEERS; q++)
-    if (g.slab[q] && q != c->rank && c->p2p_ready) cudaIpcCloseMemHandle(g.slab[q]);
+    if (g.slab[q] && q != c->rank && c->p2p_ready && c->p2p_ipc) cudaIpcCloseMemHandle(g.slab[q]);
   if (c->slab) cudaFree(c->slab);
   c->slab = nullptr;
   c->p2p_ready = false;
@@ -502,7 +508,16 @@ int finish_evolve(al26_ctx *c) {
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-int al26_version(void) { return 100; }
+int al26_version(void) { return 200; }
+
+int al26_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ndev;
+}
 
 const char *al26_last_error(al26_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
@@ -540,7 +555,7 @@ al26_ctx *al26_create(int device_id) {
             cudaMallocHost(&c->h_events, (ENR_NCOUNTERS + ENR_MAX_SOURCES) * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&c->h_rows, 4 * ENR_MAX_SOURCES * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&c->en_out, 4 * sizeof(double)) == cudaSuccess && force_kernel_setup() == cudaSuccess &&
-            loop_kernel_setup() == cudaSuccess;
+            loop_kernel_setup() == cudaSuccess && enrich_kernel_setup() == cudaSuccess;
   if (!ok) {
     fail(nullptr, AL26_ECUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
@@ -667,6 +682,45 @@ int al26_dist_p2p_import(al26_ctx *c, const void *handles, int world) {
     c->g.slab[q] = p;
   }
   c->p2p_ready = true;
+  c->p2p_ipc = true;
+  return 0;
+}
+
+int al26_dist_init_local(al26_ctx *c, int rank, int world) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return fail(c, AL26_EINVAL, "bad rank/world %d/%d", rank, world);
+  if (c->committed || c->e_committed) return fail(c, AL26_ESTATE, "al26_dist_init_local must precede commit");
+  if (world > MAX_PEERS) return fail(c, AL26_EINVAL, "peer-memory mode supports at most %d ranks", MAX_PEERS);
+  c->rank = rank;
+  c->world = world;
+  c->dist_mode = 1;
+  c->local_group = world > 1;
+  return 0;
+}
+
+int al26_dist_p2p_local_slab(al26_ctx *c, void **slab) {
+  if (!c || !slab) return AL26_EINVAL;
+  if (!is_p2p(c) || !c->committed || !c->slab) return fail(c, AL26_ESTATE, "p2p_local_slab needs a committed peer-memory context");
+  *slab = c->slab;
+  return 0;
+}
+
+int al26_dist_p2p_attach(al26_ctx *c, void *const *slabs, const int *devices, int world) {
+  if (!c || !slabs || !devices) return AL26_EINVAL;
+  if (!is_p2p(c) || !c->committed) return fail(c, AL26_ESTATE, "p2p_attach needs a committed peer-memory context");
+  if (world != c->world || world > MAX_PEERS) return fail(c, AL26_EINVAL, "p2p_attach: world %d (context %d, max %d)", world, c->world, MAX_PEERS);
+  CU(cudaSetDevice(c->device));
+  for (int q = 0; q < world; q++) {
+    if (q == c->rank) continue;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, c->device, devices[q]));
+    if (!can) return fail(c, AL26_ECUDA, "device %d cannot access device %d's memory (no NVLink / P2P path)", c->device, devices[q]);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, AL26_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", devices[q], cudaGetErrorString(e));
+    cudaGetLastError();
+    c->g.slab[q] = slabs[q];
+  }
+  c->p2p_ready = true;
+  c->p2p_ipc = false;
   return 0;
 }
 
@@ -1123,7 +1177,7 @@ int al26_grav_energies(al26_ctx *c, double *kinetic, double *potential, double *
   }
   e.block_part = c->en_scratch; e.out = c->en_out;
   c->launches += launch_energies(e, c->stream);
-  if (c->world > 1) NC(g_nccl.AllReduce(c->en_out, c->en_out, 3, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->world > 1 && !c->local_group) NC(g_nccl.AllReduce(c->en_out, c->en_out, 3, ncclDouble, ncclSum, c->comm, c->stream));
   CU(cudaMemcpyAsync(c->h_small, c->en_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (kinetic) *kinetic = c->h_small[0];
@@ -1712,6 +1766,269 @@ int al26_enrich_get(al26_ctx *c, int64_t n, double *inv, double *fin, uint8_t *d
   if (kicked) CU(cudaMemcpyAsync(kicked, e.kicked, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// al26_group: several GPUs driven from ONE host process -- what `ph4(converter, number_of_workers=k)` is to the
+// reference script (al26_nbody.py:57,1711-1720: one Python process, k MPI worker ranks behind one object).  k contexts,
+// one per GPU, each on its own persistent host thread; every call fans out to the threads and joins.  The ranks run the
+// peer-memory protocol (replicated state, owner-computes, corrected particles stored into the peers' slabs over NVLink,
+// DESIGN.md section 5) on plain peer pointers (cudaDeviceEnablePeerAccess; no IPC, no NCCL).
+// ------------------------------------------------------------------------------------------
+struct al26_group {
+  int n = 0;
+  std::vector<int> dev;
+  std::vector<al26_ctx *> ctx;
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::function<int(int)> job;
+  unsigned long long job_id = 0;
+  int pending = 0;
+  std::vector<int> rc;
+  bool quit = false;
+  std::string err;
+  int64_t n_tot = 0;
+};
+
+namespace {
+std::string g_group_error;
+
+void group_worker(al26_group *g, int r) {
+  cudaSetDevice(g->dev[r]);
+  unsigned long long seen = 0;
+  while (true) {
+    std::function<int(int)> fn;
+    {
+      std::unique_lock<std::mutex> lk(g->mu);
+      g->cv_job.wait(lk, [&] { return g->quit || g->job_id != seen; });
+      if (g->quit) return;
+      seen = g->job_id;
+      fn = g->job;
+    }
+    const int rc = fn(r);
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->rc[r] = rc;
+      if (--g->pending == 0) g->cv_done.notify_all();
+    }
+  }
+}
+
+// run fn(rank) on every GPU's thread at the same time; first failing rank's code and message
+int group_run(al26_group *g, std::function<int(int)> fn) {
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->job = std::move(fn);
+    g->pending = g->n;
+    g->job_id++;
+  }
+  g->cv_job.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(g->mu);
+    g->cv_done.wait(lk, [&] { return g->pending == 0; });
+  }
+  for (int r = 0; r < g->n; r++)
+    if (g->rc[r]) {
+      g->err = "GPU " + std::to_string(g->dev[r]) + ": " + (g->ctx[r] ? g->ctx[r]->err : std::string("no context"));
+      return g->rc[r];
+    }
+  return 0;
+}
+int gfail(al26_group *g, int code, const char *msg) {
+  if (g) g->err = msg;
+  else g_group_error = msg;
+  return code;
+}
+}  // namespace
+
+extern "C" {
+
+al26_group *al26_group_create(int n_gpus, const int *device_ids) {
+  if (n_gpus < 1 || n_gpus > MAX_PEERS) {
+    gfail(nullptr, AL26_EINVAL, "al26_group_create: between 1 and 8 GPUs");
+    return nullptr;
+  }
+  al26_group *g = new al26_group();
+  g->n = n_gpus;
+  g->dev.resize(n_gpus);
+  g->ctx.assign(n_gpus, nullptr);
+  g->rc.assign(n_gpus, 0);
+  for (int r = 0; r < n_gpus; r++) g->dev[r] = device_ids ? device_ids[r] : r;
+  for (int r = 0; r < n_gpus; r++) {
+    g->ctx[r] = al26_create(g->dev[r]);
+    if (!g->ctx[r] || al26_dist_init_local(g->ctx[r], r, n_gpus) != 0) {
+      g_group_error = std::string("al26_group_create: GPU ") + std::to_string(g->dev[r]) + ": " +
+                      (g->ctx[r] ? g->ctx[r]->err : g_create_error);
+      for (int q = 0; q <= r; q++)
+        if (g->ctx[q]) al26_destroy(g->ctx[q]);
+      delete g;
+      return nullptr;
+    }
+  }
+  for (int r = 0; r < n_gpus; r++) g->th.emplace_back(group_worker, g, r);
+  return g;
+}
+
+void al26_group_destroy(al26_group *g) {
+  if (!g) return;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->quit = true;
+  }
+  g->cv_job.notify_all();
+  for (auto &t : g->th) t.join();
+  for (al26_ctx *c : g->ctx)
+    if (c) al26_destroy(c);
+  delete g;
+}
+
+const char *al26_group_last_error(al26_group *g) { return g ? g->err.c_str() : g_group_error.c_str(); }
+int al26_group_size(al26_group *g) { return g ? g->n : 0; }
+al26_ctx *al26_group_ctx(al26_group *g, int rank) { return (g && rank >= 0 && rank < g->n) ? g->ctx[rank] : nullptr; }
+
+int al26_group_grav_set_params(al26_group *g, double eps2, double eta, double dt_max, double dt_min) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_grav_set_params(g->ctx[r], eps2, eta, dt_max, dt_min); });
+}
+
+int al26_group_grav_set_reinit_policy(al26_group *g, int policy) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_grav_set_reinit_policy(g->ctx[r], policy); });
+}
+
+int al26_group_grav_commit(al26_group *g, int64_t n, const double *m, const double *x, const double *y, const double *z,
+                           const double *vx, const double *vy, const double *vz) {
+  if (!g) return AL26_EINVAL;
+  int rc = group_run(g, [=](int r) { return al26_grav_commit(g->ctx[r], n, m, x, y, z, vx, vy, vz); });
+  if (rc || g->n == 1) {
+    if (!rc) g->n_tot = n;
+    return rc;
+  }
+  std::vector<void *> slabs(g->n, nullptr);
+  for (int r = 0; r < g->n; r++)
+    if ((rc = al26_dist_p2p_local_slab(g->ctx[r], &slabs[r]))) {
+      g->err = g->ctx[r]->err;
+      return rc;
+    }
+  rc = group_run(g, [&](int r) { return al26_dist_p2p_attach(g->ctx[r], slabs.data(), g->dev.data(), g->n); });
+  if (!rc) g->n_tot = n;
+  return rc;
+}
+
+int al26_group_grav_set_mass(al26_group *g, int64_t n, const double *m) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_grav_set_mass(g->ctx[r], n, m); });
+}
+
+int al26_group_grav_set_time(al26_group *g, double t) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_grav_set_time(g->ctx[r], t); });
+}
+
+int al26_group_grav_get_time(al26_group *g, double *t) { return g ? al26_grav_get_time(g->ctx[0], t) : AL26_EINVAL; }
+
+int al26_group_grav_evolve(al26_group *g, double t_end, int64_t *n_block_steps, int64_t *n_pairs) {
+  if (!g) return AL26_EINVAL;
+  std::vector<int64_t> steps(g->n, 0), pairs(g->n, 0);
+  const int rc = group_run(g, [&](int r) { return al26_grav_evolve(g->ctx[r], t_end, &steps[r], &pairs[r]); });
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (int r = 0; r < g->n; r++) tot += pairs[r];
+  if (n_block_steps) *n_block_steps = steps[0];  // every rank takes every block step
+  if (n_pairs) *n_pairs = tot;                   // each rank counts the pairs of the particles it owns
+  return 0;
+}
+
+int al26_group_grav_get_state(al26_group *g, int64_t n, double *m, double *x, double *y, double *z, double *vx, double *vy,
+                              double *vz) {
+  if (!g) return AL26_EINVAL;
+  const int rc = al26_grav_get_state(g->ctx[0], n, m, x, y, z, vx, vy, vz);  // the state is replicated: rank 0 has it all
+  if (rc) g->err = g->ctx[0]->err;
+  return rc;
+}
+
+int al26_group_grav_energies(al26_group *g, double *kinetic, double *potential, double *sum_mm_over_r) {
+  if (!g) return AL26_EINVAL;
+  std::vector<double> k(g->n, 0.0), u(g->n, 0.0), s(g->n, 0.0);
+  const int rc = group_run(g, [&](int r) { return al26_grav_energies(g->ctx[r], &k[r], &u[r], &s[r]); });
+  if (rc) return rc;
+  double K = 0.0, U = 0.0, S = 0.0;
+  for (int r = 0; r < g->n; r++) {  // fixed rank order: deterministic
+    K += k[r]; U += u[r]; S += s[r];
+  }
+  if (kinetic) *kinetic = K;
+  if (potential) *potential = U;
+  if (sum_mm_over_r) *sum_mm_over_r = S;
+  return 0;
+}
+
+int al26_group_last_device_ms(al26_group *g, double *ms, int64_t *kernel_launches) {
+  if (!g) return AL26_EINVAL;
+  double mx = 0.0;
+  int64_t nl = 0;
+  for (int r = 0; r < g->n; r++) {
+    mx = std::max(mx, g->ctx[r]->last_ms);
+    nl += g->ctx[r]->last_launches;
+  }
+  if (ms) *ms = mx;
+  if (kernel_launches) *kernel_launches = nl;
+  return 0;
+}
+
+int al26_group_enrich_commit(al26_group *g, int64_t n, const double *r_disk_km, const double *tau_disk_myr,
+                             const uint8_t *disk_alive, const uint8_t *kicked, const double *wr26, const double *wr60,
+                             const double *sn26_kg, const double *sn60_kg) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) {
+    return al26_enrich_commit(g->ctx[r], n, r_disk_km, tau_disk_myr, disk_alive, kicked, wr26, wr60, sn26_kg, sn60_kg);
+  });
+}
+
+int al26_group_enrich_set_units(al26_group *g, double km_per_length, double kms_per_speed) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_enrich_set_units(g->ctx[r], km_per_length, kms_per_speed); });
+}
+
+int al26_group_enrich_set_mode(al26_group *g, int mode) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_enrich_set_mode(g->ctx[r], mode); });
+}
+
+int al26_group_enrich_set_inventories(al26_group *g, int64_t n, const double *inv, const double *fin) {
+  if (!g) return AL26_EINVAL;
+  return group_run(g, [=](int r) { return al26_enrich_set_inventories(g->ctx[r], n, inv, fin); });
+}
+
+int al26_group_enrich_step(al26_group *g, int64_t n, const double *mass_msun, const double *mdot_kg_s, const double *pos_vel,
+                           double dt_s, double t_new_myr, double r_bub_local_km, double r_bub_global_km, double decay26,
+                           double decay60, int with_agb, int32_t *sn_events, int64_t sn_cap, int64_t *n_sn_events) {
+  if (!g) return AL26_EINVAL;
+  // every rank detects the same events; rank 0 reports them, the others use scratch of their own
+  std::vector<std::vector<int32_t>> scratch(g->n);
+  std::vector<int64_t> ne(g->n, 0);
+  const int rc = group_run(g, [&](int r) {
+    int32_t *ev = sn_events;
+    int64_t cap = sn_cap;
+    if (r != 0) {
+      scratch[r].resize(ENR_MAX_SOURCES);
+      ev = scratch[r].data();
+      cap = ENR_MAX_SOURCES;
+    }
+    return al26_enrich_step(g->ctx[r], n, mass_msun, mdot_kg_s, pos_vel, dt_s, t_new_myr, r_bub_local_km, r_bub_global_km,
+                            decay26, decay60, with_agb, ev, cap, &ne[r]);
+  });
+  if (rc) return rc;
+  if (n_sn_events) *n_sn_events = ne[0];
+  return 0;
+}
+
+int al26_group_enrich_get(al26_group *g, int64_t n, double *inv, double *fin, uint8_t *disk_alive, uint8_t *kicked) {
+  if (!g) return AL26_EINVAL;
+  // every rank writes its own disc slice of the caller's arrays; `kicked` is replicated: rank 0 writes it
+  return group_run(g, [=](int r) { return al26_enrich_get(g->ctx[r], n, inv, fin, disk_alive, r == 0 ? kicked : nullptr); });
 }
 
 }  // extern "C"

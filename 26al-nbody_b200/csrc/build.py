@@ -9,7 +9,10 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libal26b200.so")
+# AL26_BUILD_TAG=timing (with AL26_NVCC_EXTRA="-DAL26_FUSE_TIMING") builds a second, instrumented library next to the
+# product one: libal26b200_timing.so, objects under build_timing/; select it at run time with AL26_LIB=<path>
+TAG = os.environ.get("AL26_BUILD_TAG", "")
+SO = os.path.join(HERE, "libal26b200" + ("_" + TAG if TAG else "") + ".so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"] + ARCH
 COMMON += os.environ.get("AL26_NVCC_EXTRA", "").split()  # e.g. -DAL26_FUSE_TIMING (diagnostic builds)
@@ -41,7 +44,7 @@ def build(force=False, verbose=False):
     deps = [os.path.join(HERE, d) for d in DEPS] + [os.path.abspath(__file__)]
     for src, extra in UNITS:
         s = os.path.join(HERE, src)
-        o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        o = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""), src.replace(".cu", ".o"))
         os.makedirs(os.path.dirname(o), exist_ok=True)
         if force or _newer(o, [s] + deps):
             cmd = [nvcc] + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]

@@ -238,8 +238,9 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
   }
   const double inv_h = 1.0 / h;
   const int ncell = gd[0] * gd[1] * gd[2];
-  int *start = e.cell_start, *cursor = e.cell_start + (ENR_GRID_CELLS + 1);
-  for (int c = tid; c <= ncell; c += SRC_T) start[c] = 0;
+  // counts -> starts -> scatter cursors all live in (dynamic) shared memory: one CTA, no global round trips
+  extern __shared__ int cells[];  // [ncell + 1]
+  for (int c = tid; c <= ncell; c += SRC_T) cells[c] = 0;
   __syncthreads();
   for (int pass = 0; pass < 2; pass++) {
     for (int k = tid; k < n_hm; k += SRC_T) {
@@ -250,17 +251,17 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
         for (int dy = -1; dy <= 1; dy++)
           for (int dx = -1; dx <= 1; dx++) {
             const int cell = ((cz + dz) * gd[1] + (cy + dy)) * gd[0] + (cx + dx);
-            if (pass == 0) atomicAdd(&start[cell + 1], 1);  // counts shifted by one: the scan leaves the starts
-            else e.cell_items[atomicAdd(&cursor[cell], 1)] = k;
+            if (pass == 0) atomicAdd(&cells[cell + 1], 1);  // counts shifted by one: the scan leaves the starts
+            else e.cell_items[atomicAdd(&cells[cell], 1)] = k;
           }
     }
     __syncthreads();
     if (pass == 1) break;
-    {  // inclusive scan of start[1..ncell] in place (each thread a contiguous run, then the block's run totals)
+    {  // inclusive scan of cells[1..ncell] in place (each thread a contiguous run, then the block's run totals)
       const int per = (ncell + SRC_T - 1) / SRC_T;
       const int b = 1 + tid * per, en = min(ncell + 1, b + per);
       int run = 0;
-      for (int c = b; c < en; c++) run += __ldcg(&start[c]);
+      for (int c = b; c < en; c++) run += cells[c];
       const int lane = tid & 31, warp = tid >> 5;
       int incl = run;
 #pragma unroll
@@ -273,12 +274,12 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
       int off = incl - run;
       for (int w = 0; w < warp; w++) off += shi[w];
       for (int c = b; c < en; c++) {
-        off += __ldcg(&start[c]);
-        start[c] = off;
+        off += cells[c];
+        cells[c] = off;
       }
     }
     __syncthreads();
-    for (int c = tid; c < ncell; c += SRC_T) cursor[c] = __ldcg(&start[c]);
+    for (int c = tid; c <= ncell; c += SRC_T) e.cell_start[c] = cells[c];  // the scatter below turns cells[] into cursors
     __syncthreads();
   }
   if (tid == 0) {
@@ -566,6 +567,11 @@ int launch_interloper(const EnrichDev &e, const InterloperParams &p, cudaStream_
   return 1;
 }
 
+cudaError_t enrich_kernel_setup() {
+  return cudaFuncSetAttribute(k_enrich_sources, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((ENR_GRID_CELLS + 1) * sizeof(int)));
+}
+
 int enrich_sources_grid(int n_tot, int sm_count) {
   int g = (n_tot + SRC_T - 1) / SRC_T;
   const int cap = sm_count > 0 ? 2 * sm_count : 296;
@@ -580,8 +586,9 @@ int launch_enrich_classify(const EnrichDev &e, const EnrichParams &p, int sm_cou
 
 // tables_only: the source list is already on the device (sorted) and the compact rows e.hm_rows are filled
 int launch_enrich(const EnrichDev &e, const EnrichParams &p, int sm_count, bool tables_only, cudaStream_t s, cudaError_t *err) {
-  if (tables_only) k_enrich_sources<<<1, SRC_T, 0, s>>>(e, p, 2);
-  else k_enrich_sources<<<enrich_sources_grid(e.n_tot, sm_count), SRC_T, 0, s>>>(e, p, 0);
+  const size_t dsm = (p.mode == 2) ? (size_t)(ENR_GRID_CELLS + 1) * sizeof(int) : 0;  // the cell array of the list build
+  if (tables_only) k_enrich_sources<<<1, SRC_T, dsm, s>>>(e, p, 2);
+  else k_enrich_sources<<<enrich_sources_grid(e.n_tot, dsm ? sm_count / 2 : sm_count), SRC_T, dsm, s>>>(e, p, 0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((e.n_loc + EN_T - 1) / EN_T);
   cfg.blockDim = dim3(EN_T);

@@ -146,25 +146,27 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
 
 def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, max_outer_steps=None, verbose=False,
         device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None,
-        epsilon=None, progress=None, step_mode=None):
+        epsilon=None, progress=None, step_mode=None, number_of_workers=1):
     """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200".
-    step_mode: None = library default (CUDA graph); 2 = graph + cluster engine (small N, see include/al26_b200.h)."""
+    step_mode: None = the library's automatic choice (graph + cluster engine when the particles fit one cluster, else
+    the CUDA graph); 0 / 1 / 2 force the graph / the persistent loop kernel / the cluster engine (include/al26_b200.h).
+    number_of_workers: GPUs driven from this process (the script's `workers`, al26_nbody.py:57)."""
     from .gravity import B200Gravity
     from .gravity import GravityCore
     from . import _lib
     stellar = stellar or StellarStub()
-    ctx = _lib.Context(device)
-    if step_mode is not None:
+    ctx = _lib.Group(number_of_workers) if number_of_workers > 1 else _lib.Context(device)
+    if step_mode is not None and number_of_workers == 1:
         ctx.set_step_mode(step_mode)
     pot = None
     if model == "fractal" and nstars > 2000:
         def pot(m, x, y, z):  # the fractal generator's virial scaling needs U: use the device pair reduction
-            g0 = GravityCore(ctx=ctx)
+            g0 = GravityCore(ctx=ctx if number_of_workers == 1 else _lib.Context(device))
             g0.commit(m, x, y, z, np.zeros_like(x), np.zeros_like(x), np.zeros_like(x))
             return g0.energies()[1]
     cluster, converter = init_cluster(model, nstars, Rc, yields=yields, stellar=stellar, seed=seed,
                                       fractal_dimension=fractal_dimension, potential_energy=pot)
-    gravity = B200Gravity(converter, ctx=ctx)
+    gravity = B200Gravity(converter, number_of_workers=number_of_workers, ctx=ctx)
     if epsilon is not None:  # the script never sets it (ph4 default 0); sub-virial fractals need it, see DESIGN.md
         gravity.parameters.epsilon_squared = epsilon * epsilon
     gravity.particles.add_particles(cluster)                                      # :1728

@@ -40,13 +40,17 @@ class EnrichCore:
         self.ctx = ctx if ctx is not None else _lib.Context(device)
         self.L = self.ctx.L
         self.h = self.ctx.h
+        self.grouped = isinstance(self.ctx, _lib.Group)  # several GPUs from this process: discs sharded inside the library
         self.n = 0
+
+    def _f(self, name):
+        return getattr(self.L, ("al26_group_" if self.grouped else "al26_") + name)
 
     def commit(self, r_disk_km, tau_disk_myr, disk_alive, kicked, wr26, wr60, sn26_kg, sn60_kg):
         """Per-star attributes of init_cluster (al26_nbody.py:1543-1603); inventories start at 0."""
         n = len(r_disk_km)
         u8 = lambda a: np.ascontiguousarray(np.asarray(a).astype(bool), dtype=np.uint8)
-        self.ctx.chk(self.L.al26_enrich_commit(
+        self.ctx.chk(self._f("enrich_commit")(
             self.h, n, _lib.f64(r_disk_km), _lib.f64(tau_disk_myr), u8(disk_alive), u8(kicked),
             _lib.f64(wr26), _lib.f64(wr60), _lib.f64(sn26_kg), _lib.f64(sn60_kg)))
         self.n = n
@@ -55,16 +59,16 @@ class EnrichCore:
     def set_inventories(self, inv=None, fin=None):
         inv = None if inv is None else _lib.f64(inv)
         fin = None if fin is None else _lib.f64(fin)
-        self.ctx.chk(self.L.al26_enrich_set_inventories(self.h, self.n, _lib.ptr(inv), _lib.ptr(fin)))
+        self.ctx.chk(self._f("enrich_set_inventories")(self.h, self.n, _lib.ptr(inv), _lib.ptr(fin)))
 
     def set_mode(self, mode):
         """0 exact (bit-identical to the reference kernel; default), 1 fast (tolerance 1e-10: hoisted global sum,
         4-instruction pair test), 2 fast + cell-grid pruning (see include/al26_b200.h)"""
         mode = {"exact": 0, "fast": 1, "pruned": 2}.get(mode, mode)
-        self.ctx.chk(self.L.al26_enrich_set_mode(self.h, int(mode)))
+        self.ctx.chk(self._f("enrich_set_mode")(self.h, int(mode)))
 
     def set_units(self, km_per_length, kms_per_speed):
-        self.ctx.chk(self.L.al26_enrich_set_units(self.h, float(km_per_length), float(kms_per_speed)))
+        self.ctx.chk(self._f("enrich_set_units")(self.h, float(km_per_length), float(kms_per_speed)))
 
     def step(self, mass_msun, mdot_kg_s, pos_vel, dt_s, t_new_myr, r_bub_local_km, r_bub_global_km,
              decay26, decay60, with_agb=False):
@@ -75,7 +79,7 @@ class EnrichCore:
         if pv is not None and pv.shape != (6, self.n):
             raise ValueError(f"pos_vel must have shape (6, {self.n})")
         ne = C.c_int64(0)
-        self.ctx.chk(self.L.al26_enrich_step(
+        self.ctx.chk(self._f("enrich_step")(
             self.h, self.n, _lib.f64(mass_msun), _lib.f64(mdot_kg_s), _lib.ptr(pv), float(dt_s), float(t_new_myr),
             float(r_bub_local_km), float(r_bub_global_km), float(decay26), float(decay60), int(bool(with_agb)),
             self._sn, len(self._sn), C.byref(ne)))
@@ -101,7 +105,7 @@ class EnrichCore:
         fin = np.zeros((NINV, self.n)) if want_fin else None
         alive = np.zeros(self.n, dtype=np.uint8)
         kicked = np.zeros(self.n, dtype=np.uint8)
-        self.ctx.chk(self.L.al26_enrich_get(self.h, self.n, _lib.ptr(inv), _lib.ptr(fin), _lib.ptr(alive),
+        self.ctx.chk(self._f("enrich_get")(self.h, self.n, _lib.ptr(inv), _lib.ptr(fin), _lib.ptr(alive),
                                             _lib.ptr(kicked)))
         return inv, fin, alive.astype(bool), kicked.astype(bool)
 

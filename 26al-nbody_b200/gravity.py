@@ -23,18 +23,25 @@ from .particles import Particles
 
 
 class GravityCore:
-    """Hermite-4 block-timestep direct N-body on one GPU (or one rank of a multi-GPU job)."""
+    """Hermite-4 block-timestep direct N-body on one GPU (or one rank of a multi-GPU job), or -- given a
+    `_lib.Group` -- on several GPUs driven from this one process (the reference-surface methods only; the parity
+    hooks below need a single context)."""
 
     def __init__(self, device=0, ctx=None, eps2=0.0, eta=0.14, dt_max=0.125, dt_min=2.0 ** -40):
         self.ctx = ctx if ctx is not None else _lib.Context(device)
         self.L = self.ctx.L
         self.h = self.ctx.h
+        self.grouped = isinstance(self.ctx, _lib.Group)
         self.n = 0
         self.set_params(eps2, eta, dt_max, dt_min)
 
+    def _f(self, name):
+        """the C entry point `al26_<name>`, or its `al26_group_<name>` twin when this core drives a group"""
+        return getattr(self.L, ("al26_group_" if self.grouped else "al26_") + name)
+
     # -- reference surface ------------------------------------------------------------------
     def set_params(self, eps2=0.0, eta=0.14, dt_max=0.125, dt_min=2.0 ** -40):
-        self.ctx.chk(self.L.al26_grav_set_params(self.h, eps2, eta, dt_max, dt_min))
+        self.ctx.chk(self._f("grav_set_params")(self.h, eps2, eta, dt_max, dt_min))
         self.params = dict(eps2=eps2, eta=eta, dt_max=dt_max, dt_min=dt_min)
 
     def commit(self, m, x, y, z, vx, vy, vz):
@@ -42,39 +49,39 @@ class GravityCore:
         n = len(arrs[0])
         if any(len(a) != n for a in arrs):
             raise ValueError("commit: arrays differ in length")
-        self.ctx.chk(self.L.al26_grav_commit(self.h, n, *arrs))
+        self.ctx.chk(self._f("grav_commit")(self.h, n, *arrs))
         self.n = n
-        self.ctx.p2p_connect()  # multi-GPU peer-memory mode: swap the staging slabs' IPC handles
+        self.ctx.p2p_connect()  # multi-process peer-memory mode: swap the staging slabs' IPC handles
 
     def set_mass(self, m):
-        self.ctx.chk(self.L.al26_grav_set_mass(self.h, len(m), _lib.f64(m)))
+        self.ctx.chk(self._f("grav_set_mass")(self.h, len(m), _lib.f64(m)))
 
     def set_reinit_policy(self, policy):
         """mass-only update: 0 = recompute forces, keep timesteps (default, ph4's recommit); 1 = forces + initial timesteps"""
-        self.ctx.chk(self.L.al26_grav_set_reinit_policy(self.h, int(policy)))
+        self.ctx.chk(self._f("grav_set_reinit_policy")(self.h, int(policy)))
 
     def set_time(self, t):
-        self.ctx.chk(self.L.al26_grav_set_time(self.h, float(t)))
+        self.ctx.chk(self._f("grav_set_time")(self.h, float(t)))
 
     def get_time(self):
         t = C.c_double(0)
-        self.ctx.chk(self.L.al26_grav_get_time(self.h, C.byref(t)))
+        self.ctx.chk(self._f("grav_get_time")(self.h, C.byref(t)))
         return t.value
 
     def evolve(self, t_end):
         """Advance to t_end (every particle synchronised there).  Returns (block steps, pairs)."""
         ns, npairs = C.c_int64(0), C.c_int64(0)
-        self.ctx.chk(self.L.al26_grav_evolve(self.h, float(t_end), C.byref(ns), C.byref(npairs)))
+        self.ctx.chk(self._f("grav_evolve")(self.h, float(t_end), C.byref(ns), C.byref(npairs)))
         return ns.value, npairs.value
 
     def get_state(self, out=None):
         out = out if out is not None else [np.empty(self.n) for _ in range(7)]
-        self.ctx.chk(self.L.al26_grav_get_state(self.h, self.n, *out))
+        self.ctx.chk(self._f("grav_get_state")(self.h, self.n, *out))
         return out
 
     def energies(self):
         k, u, s = C.c_double(0), C.c_double(0), C.c_double(0)
-        self.ctx.chk(self.L.al26_grav_energies(self.h, C.byref(k), C.byref(u), C.byref(s)))
+        self.ctx.chk(self._f("grav_energies")(self.h, C.byref(k), C.byref(u), C.byref(s)))
         return k.value, u.value, s.value
 
     # -- parity hooks -----------------------------------------------------------------------
@@ -262,15 +269,21 @@ class _ParticleView:
 class B200Gravity:
     """Drop-in for `ph4(converter, number_of_workers=workers)` (al26_nbody.py:1715-1717).
 
-    `number_of_workers` is accepted for signature compatibility; GPUs are one process each
-    (torch.distributed), so inside one process the worker count is the process's world size.
+    `number_of_workers` is the number of GPUs this ONE process drives (the reference's worker count, :57): 1 = one
+    context on `device`; k > 1 = an `al26_group` of k GPUs (`devices`, default 0..k-1), one host thread per GPU
+    inside the library, peer-memory exchange over NVLink.  A job that is already one process per GPU (torchrun)
+    passes its joined `ctx` instead (dist.init_context) and leaves number_of_workers at 1.
     """
 
-    def __init__(self, converter, number_of_workers=1, device=0, ctx=None, **_ignored):
+    def __init__(self, converter, number_of_workers=1, device=0, ctx=None, devices=None, **_ignored):
         self.converter = converter
         self._len_si = converter.length_si
-        # multi-GPU: pass a Context already joined to the job (dist.init_context); one process per GPU
-        self._core = GravityCore(ctx=ctx if ctx is not None else _lib.Context(device))
+        number_of_workers = int(number_of_workers)
+        if number_of_workers < 1:
+            raise ValueError("number_of_workers must be >= 1")
+        if ctx is None:
+            ctx = _lib.Group(number_of_workers, devices) if number_of_workers > 1 else _lib.Context(device)
+        self._core = GravityCore(ctx=ctx)
         self._cache = None
         self.particles = _GravityParticles(self)
         self.parameters = _Parameters(self)

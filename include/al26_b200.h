@@ -51,6 +51,7 @@ al26_ctx *al26_create(int device_id);
 void al26_destroy(al26_ctx *ctx);
 const char *al26_last_error(al26_ctx *ctx); /* ctx may be NULL: message of a failed al26_create */
 int al26_version(void);
+int al26_device_count(void); /* usable CUDA devices (0 without a driver / GPU) */
 /* device info for the host shim / bench: SM count, clock (kHz), free and total bytes */
 int al26_device_info(al26_ctx *ctx, int *sm_count, int *clock_khz, int64_t *free_bytes, int64_t *total_bytes);
 
@@ -75,6 +76,51 @@ int al26_dist_set_split_min(al26_ctx *ctx, int n_act_min);
  * the host all-gather the handles (torch.distributed), import the world x 64 bytes */
 int al26_dist_p2p_export(al26_ctx *ctx, void *out64);
 int al26_dist_p2p_import(al26_ctx *ctx, const void *handles, int world);
+
+/* the same peer-memory protocol between contexts of ONE process (what al26_group below does): join without NCCL,
+ * then hand every rank the others' slab pointers; peer access is enabled here (cudaDeviceEnablePeerAccess).
+ * Energies then return this rank's partial sums (the caller adds them up). */
+int al26_dist_init_local(al26_ctx *ctx, int rank, int world);
+int al26_dist_p2p_local_slab(al26_ctx *ctx, void **slab);
+int al26_dist_p2p_attach(al26_ctx *ctx, void *const *slabs, const int *devices, int world);
+
+/* ---- several GPUs from one process ------------------------------------------------------
+ * replaces: `ph4(converter, number_of_workers=workers)` (al26_nbody.py:57,1711-1720) -- ONE script process, `workers`
+ * worker ranks behind one object.  A group owns n_gpus contexts, one per GPU, each on its own host thread; every
+ * call below fans out to all of them and joins (the ranks' kernels must run at the same time: they exchange
+ * corrected particles and barrier flags over NVLink).  Arguments as for the single-context calls; host arrays are
+ * global length.  device_ids may be NULL (GPUs 0..n_gpus-1).  n must be divisible by n_gpus. */
+typedef struct al26_group al26_group;
+al26_group *al26_group_create(int n_gpus, const int *device_ids);
+void al26_group_destroy(al26_group *grp);
+const char *al26_group_last_error(al26_group *grp); /* grp may be NULL: message of a failed al26_group_create */
+int al26_group_size(al26_group *grp);
+al26_ctx *al26_group_ctx(al26_group *grp, int rank); /* tuning hooks / diagnostics of one rank (before commit) */
+int al26_group_grav_set_params(al26_group *grp, double eps2, double eta, double dt_max, double dt_min);
+int al26_group_grav_set_reinit_policy(al26_group *grp, int policy);
+int al26_group_grav_commit(al26_group *grp, int64_t n, const double *m, const double *x, const double *y, const double *z,
+                           const double *vx, const double *vy, const double *vz);
+int al26_group_grav_set_mass(al26_group *grp, int64_t n, const double *m);
+int al26_group_grav_set_time(al26_group *grp, double t);
+int al26_group_grav_get_time(al26_group *grp, double *t);
+/* n_block_steps: block steps of the call; n_pairs: pair evaluations summed over the GPUs */
+int al26_group_grav_evolve(al26_group *grp, double t_end, int64_t *n_block_steps, int64_t *n_pairs);
+int al26_group_grav_get_state(al26_group *grp, int64_t n, double *m, double *x, double *y, double *z, double *vx,
+                              double *vy, double *vz);
+int al26_group_grav_energies(al26_group *grp, double *kinetic, double *potential, double *sum_mm_over_r);
+/* device time of the last evolve / enrich_step: the slowest GPU's; kernel launches: all GPUs' */
+int al26_group_last_device_ms(al26_group *grp, double *ms, int64_t *kernel_launches);
+int al26_group_enrich_commit(al26_group *grp, int64_t n, const double *r_disk_km, const double *tau_disk_myr,
+                             const uint8_t *disk_alive, const uint8_t *kicked, const double *wr26, const double *wr60,
+                             const double *sn26_kg, const double *sn60_kg);
+int al26_group_enrich_set_units(al26_group *grp, double km_per_length, double kms_per_speed);
+int al26_group_enrich_set_mode(al26_group *grp, int mode);
+int al26_group_enrich_set_inventories(al26_group *grp, int64_t n, const double *inv, const double *fin);
+int al26_group_enrich_step(al26_group *grp, int64_t n, const double *mass_msun, const double *mdot_kg_s,
+                           const double *pos_vel, double dt_s, double t_new_myr, double r_bub_local_km,
+                           double r_bub_global_km, double decay26, double decay60, int with_agb, int32_t *sn_events,
+                           int64_t sn_cap, int64_t *n_sn_events);
+int al26_group_enrich_get(al26_group *grp, int64_t n, double *inv, double *fin, uint8_t *disk_alive, uint8_t *kicked);
 
 /* diagnostic, peer-memory mode: where a rank's time goes, in SM cycles of CTA 0 since the last commit (12 values):
  * [0] fused redundant steps, [1] their number, [2] other redundant steps, [3] their number, [4] their active

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     lib_mod = importlib.import_module("26al-nbody_b200._lib")
     assert declared == set(lib_mod.SIGNATURES), "ctypes prototypes and header disagree"
-    assert L.al26_version() == 100
+    assert L.al26_version() == 200
 
 
 def test_oracle_is_not_reachable_from_the_product(pkg):
