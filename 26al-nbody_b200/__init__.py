@@ -13,7 +13,7 @@ from .gravity import GravityCore, B200Gravity  # noqa: F401
 from .enrichment import EnrichCore, decay_fractions, NINV, ROWS, ROW  # noqa: F401
 from . import ic  # noqa: F401
 from . import dist  # noqa: F401
-from . import stellar, driver  # noqa: F401
+from . import stellar, driver, checkpoint  # noqa: F401
 from .stellar import StellarStub, YieldTables  # noqa: F401
 from .yields_io import Yields  # noqa: F401
 

@@ -753,7 +753,8 @@ int al26_grav_commit(al26_ctx *c, int64_t n, const double *m, const double *x, c
   if (!c) return AL26_EINVAL;
   if (n <= 0 || n > 0x7fffffff / 2) return fail(c, AL26_EINVAL, "particle count %lld out of range", (long long)n);
   if (!m || !x || !y || !z || !vx || !vy || !vz) return fail(c, AL26_EINVAL, "null array");
-  if (n % c->world) return fail(c, AL26_EINVAL, "particle count %lld not divisible by world size %d", (long long)n, c->world);
+  if (c->world > 1 && !is_p2p(c) && n % c->world)  // the all-gather wants equal slices; the peer-memory mode owns i % world and takes any n
+    return fail(c, AL26_EINVAL, "NCCL mode: particle count %lld not divisible by world size %d", (long long)n, c->world);
   if (c->in_evolve) return fail(c, AL26_ESTATE, "commit during evolve");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
@@ -1521,7 +1522,6 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   if (n <= 0 || n > 0x7fffffff / 2) return fail(c, AL26_EINVAL, "star count %lld out of range", (long long)n);
   if (!r_disk_km || !tau_disk_myr || !disk_alive || !kicked || !wr26 || !wr60 || !sn26 || !sn60)
     return fail(c, AL26_EINVAL, "null array");
-  if (n % c->world) return fail(c, AL26_EINVAL, "star count %lld not divisible by world size %d", (long long)n, c->world);
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   free_enrich(c);

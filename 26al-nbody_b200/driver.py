@@ -48,6 +48,7 @@ def init_cluster(model, nstars, Rc, yields=None, stellar=None, no_massive_star_r
         setattr(cl, a, converter.speed_to_si(c[a]))
     cl.radius = np.zeros(nstars) | U.au                                # :1542
     cl.kicked = np.zeros(nstars, dtype=bool)                           # :1543
+    cl.zams_mass = m | U.MSun  # not in the reference's set: lets the stellar STUB resume from a checkpoint exactly
     cl.r_disk = np.full(nstars, r_disk) | U.au                         # :1547
     cl.tau_disk = c["tau_disk_myr"] | U.Myr                            # :1548
     for col in list(INVENTORY_COLUMNS) + [k + "_final" for k in INVENTORY_COLUMNS]:
@@ -75,6 +76,18 @@ def make_enrichment(gravity, cluster, converter):
     return e
 
 
+def push_inventories(enrich, cluster):
+    """cluster columns -> device inventories (resume from a checkpoint, al26_nbody.py:1641-1656): the inverse of
+    pull_inventories; disk_alive / kicked go in through make_enrichment's commit."""
+    n = len(cluster)
+    inv = np.zeros((len(ROW), n))
+    fin = np.zeros((len(ROW), n))
+    for col, row in INVENTORY_COLUMNS.items():
+        inv[ROW[row]] = U.value_in(getattr(cluster, col), U.kg)
+        fin[ROW[row]] = U.value_in(getattr(cluster, col + "_final"), U.kg)
+    enrich.set_inventories(inv, fin)
+
+
 def pull_inventories(enrich, cluster):
     """Device inventories -> cluster columns (what the script's yields / checkpoints read, :1097-1105)."""
     inv, fin, alive, kicked = enrich.get()
@@ -89,7 +102,7 @@ def pull_inventories(enrich, cluster):
 
 
 def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=False, verbose=False, log=print,
-                      sync_cluster=True, yields=None):
+                      sync_cluster=True, yields=None, metadata=None):
     """One outer step (al26_nbody.py:704-1113).  Returns (finish, info)."""
     tm = {}
     t0 = time.perf_counter()
@@ -133,8 +146,13 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
     tm["discs"] = time.perf_counter() - t1
     if save:
         pull_inventories(enrich, cluster)
+        if metadata is not None:
+            metadata.update(t_new)                                                # :1099
         if yields is not None:
             yields.update_state(gravity.model_time, cluster)                      # :1101
+        if metadata is not None:                                                  # :1103-1105
+            from .checkpoint import save_checkpoint
+            save_checkpoint(metadata.filename, metadata.most_recent_checkpoint, cluster, converter, yields, metadata)
     tm["step"] = time.perf_counter() - t0
     if verbose:
         log("t = {:.3f} Myr: grav {:.3f} s, stel {:.3f} s, discs {:.3f} s, step {:.3f} s".format(
@@ -146,45 +164,69 @@ def evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=Fa
 
 def run(nstars=1000, Rc=1.0 | U.pc, t_f=10.0 | U.Myr, model="plummer", seed=0, max_outer_steps=None, verbose=False,
         device=0, fractal_dimension=1.6, yields=None, stellar=None, log=print, yields_file=None,
-        epsilon=None, progress=None, step_mode=None, number_of_workers=1):
+        epsilon=None, progress=None, step_mode=None, number_of_workers=1, checkpoint_base=None, reload=None,
+        n_checkpoint=None, reinit_policy=None):
     """`main()` of the script (al26_nbody.py:1612-1766) with gravity_model == "b200".
     step_mode: None = the library's automatic choice (graph + cluster engine when the particles fit one cluster, else
     the CUDA graph); 0 / 1 / 2 force the graph / the persistent loop kernel / the cluster engine (include/al26_b200.h).
-    number_of_workers: GPUs driven from this process (the script's `workers`, al26_nbody.py:57)."""
+    number_of_workers: GPUs driven from this process (the script's `workers`, al26_nbody.py:57).
+    checkpoint_base: write <base>-state-NNNNN / <base>-yields.* on save steps (every 10th outer step, :1755-1758) like
+    the script (checkpoint.py); reload = <base> [+ n_checkpoint]: resume from such a checkpoint (`-r base -nc k`)."""
     from .gravity import B200Gravity
     from .gravity import GravityCore
     from . import _lib
+    from . import checkpoint as ck
     stellar = stellar or StellarStub()
     ctx = _lib.Group(number_of_workers) if number_of_workers > 1 else _lib.Context(device)
     if step_mode is not None and number_of_workers == 1:
         ctx.set_step_mode(step_mode)
-    pot = None
-    if model == "fractal" and nstars > 2000:
-        def pot(m, x, y, z):  # the fractal generator's virial scaling needs U: use the device pair reduction
-            g0 = GravityCore(ctx=ctx if number_of_workers == 1 else _lib.Context(device))
-            g0.commit(m, x, y, z, np.zeros_like(x), np.zeros_like(x), np.zeros_like(x))
-            return g0.energies()[1]
-    cluster, converter = init_cluster(model, nstars, Rc, yields=yields, stellar=stellar, seed=seed,
-                                      fractal_dimension=fractal_dimension, potential_energy=pot)
+    metadata = None
+    ybook = None
+    if reload:                                                                    # :1641-1656
+        nfile = ck.most_recent_checkpoint(reload) if n_checkpoint is None else n_checkpoint
+        cluster, converter, ybook, metadata = ck.load_checkpoint(reload, nfile)
+        metadata.update_access_time()
+        if t_f is None:
+            t_f = metadata.t_f
+    else:
+        pot = None
+        if model == "fractal" and nstars > 2000:
+            def pot(m, x, y, z):  # the fractal generator's virial scaling needs U: use the device pair reduction
+                g0 = GravityCore(ctx=ctx if number_of_workers == 1 else _lib.Context(device))
+                g0.commit(m, x, y, z, np.zeros_like(x), np.zeros_like(x), np.zeros_like(x))
+                return g0.energies()[1]
+        cluster, converter = init_cluster(model, nstars, Rc, yields=yields, stellar=stellar, seed=seed,
+                                          fractal_dimension=fractal_dimension, potential_energy=pot)
     gravity = B200Gravity(converter, number_of_workers=number_of_workers, ctx=ctx)
+    if reinit_policy is not None:
+        gravity._core.set_reinit_policy(reinit_policy)
     if epsilon is not None:  # the script never sets it (ph4 default 0); sub-virial fractals need it, see DESIGN.md
         gravity.parameters.epsilon_squared = epsilon * epsilon
     gravity.particles.add_particles(cluster)                                      # :1728
     stellar.particles.add_particles(cluster)                                      # :1731
     enrich = make_enrichment(gravity, cluster, converter)
+    if reload:                                                                    # :1734-1737
+        gravity.model_time = metadata.time
+        stellar.model_time = metadata.time
+        stellar.evolve_model(metadata.time)  # the STUB's mdot(t) is a function of its clock; SeBa is left as the script leaves it
+        push_inventories(enrich, cluster)
     history = []
     n_iter = 0
     finish = False
-    ybook = None
-    if yields_file is not None:                                                   # Yields(filename) + first state (:1741)
-        from .yields_io import Yields
-        ybook = Yields(yields_file)
-        pull_inventories(enrich, cluster)
-        ybook.update_state(gravity.model_time, cluster)
+    if not reload:
+        if yields_file is not None or checkpoint_base is not None:                # Yields(filename) + first state (:1739-1745)
+            from .yields_io import Yields
+            base = checkpoint_base if checkpoint_base is not None else yields_file
+            ybook = Yields(base)
+            pull_inventories(enrich, cluster)
+            ybook.update_state(gravity.model_time, cluster)
+        if checkpoint_base is not None:
+            metadata = ck.Metadata(t_f=t_f, model=model, nstars=nstars, cluster_radius=Rc, filename=checkpoint_base)
+            ck.save_checkpoint(metadata.filename, 0, cluster, converter, ybook, metadata)
     while not finish:                                                             # :1754-1760
         save = (n_iter % 10 == 0)
         finish, info = evolve_simulation(cluster, converter, gravity, stellar, enrich, t_f, save=save,
-                                         verbose=verbose, log=log, yields=ybook)
+                                         verbose=verbose, log=log, yields=ybook, metadata=metadata)
         history.append(info)
         if progress is not None:
             progress(n_iter, info)

@@ -282,6 +282,16 @@ class B200Gravity:
         if number_of_workers < 1:
             raise ValueError("number_of_workers must be >= 1")
         if ctx is None:
+            if number_of_workers > 1 and devices is None:
+                # the script hard-codes workers = 8 (:57); like an MPI job on a smaller machine, make do with what is there
+                have = _lib.device_count()
+                if have < 1:
+                    raise _lib.Al26Error(-7, "no CUDA device -- the B200 path has no CPU fallback")
+                usable = min(number_of_workers, have, 8)
+                if usable < number_of_workers:
+                    import warnings
+                    warnings.warn(f"number_of_workers={number_of_workers} but {have} GPU(s) visible: using {usable}")
+                number_of_workers = usable
             ctx = _lib.Group(number_of_workers, devices) if number_of_workers > 1 else _lib.Context(device)
         self._core = GravityCore(ctx=ctx)
         self._cache = None

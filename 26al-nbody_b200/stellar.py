@@ -123,7 +123,10 @@ class StellarStub:
     def _install(self, cluster):
         n = len(cluster)
         p = Particles(n, keys=np.array(cluster.key, copy=True))
-        self._m0 = np.array(U.value_in(cluster.mass, U.MSun), dtype=np.float64, copy=True)
+        # a checkpointed cluster carries evolved masses; the stub's mass(t) is a function of the ZERO-AGE mass, which
+        # driver.init_cluster keeps in an extra column so that a resumed run continues exactly
+        m0 = getattr(cluster, "zams_mass", None)
+        self._m0 = np.array(U.value_in(m0 if m0 is not None else cluster.mass, U.MSun), dtype=np.float64, copy=True)
         self._life = self.lifetime_factor * approx_lifespan_myr(self._m0)
         self._massive = self._m0 >= 13.0
         self._rate = np.where(self._massive, self.wind_loss_fraction * self._m0 / self._life, 0.0)  # Msun / Myr

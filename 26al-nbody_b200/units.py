@@ -53,6 +53,12 @@ class Unit:
     def __repr__(self):
         return self.name or f"Unit({self.factor}, {self.dims})"
 
+    def __eq__(self, o):  # value semantics: a unit that went through a pickle (checkpoint.py) equals the original
+        return isinstance(o, Unit) and self.factor == o.factor and self.dims == o.dims
+
+    def __hash__(self):
+        return hash((self.factor, self.dims))
+
 
 class Quantity:
     """A number (scalar or ndarray) with a unit."""

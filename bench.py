@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--step-mode", type=int, default=-1, choices=[-1, 0, 1, 2], help="1 GPU: -1 = library default (graph; + cluster engine when N fits one cluster), 0 = CUDA graph, 1 = persistent loop kernel, 2 = graph + cluster engine")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     ap.add_argument("--no-config4", action="store_true", help="skip the N=1e6 gravity-only sub-record (BASELINE config 4)")
-    ap.add_argument("--config4-dt-myr", type=float, default=4.0e-4, help="outer step of the config-4 evolve (forced full-N sync < 10 %% of its pairs)")
+    ap.add_argument("--config4-dt-myr", type=float, default=5.0e-4, help="outer step of the config-4 evolve (forced full-N sync < 10 %% of its pairs)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity sub-record (same call on one GPU inside the job)")
     ap.add_argument("--reinit-policy", type=int, default=0, choices=[0, 1], help="e2e arm: what the per-step mass channel costs (0 = forces only, ph4's recommit; 1 = forces + initial timesteps)")
     return ap.parse_args()

@@ -89,7 +89,7 @@ int al26_dist_p2p_attach(al26_ctx *ctx, void *const *slabs, const int *devices, 
  * worker ranks behind one object.  A group owns n_gpus contexts, one per GPU, each on its own host thread; every
  * call below fans out to all of them and joins (the ranks' kernels must run at the same time: they exchange
  * corrected particles and barrier flags over NVLink).  Arguments as for the single-context calls; host arrays are
- * global length.  device_ids may be NULL (GPUs 0..n_gpus-1).  n must be divisible by n_gpus. */
+ * global length.  device_ids may be NULL (GPUs 0..n_gpus-1).  Any n (a rank owns the particles i % n_gpus == rank). */
 typedef struct al26_group al26_group;
 al26_group *al26_group_create(int n_gpus, const int *device_ids);
 void al26_group_destroy(al26_group *grp);

@@ -124,6 +124,41 @@ def test_initial_conditions(pkg):
         ic.cluster(10, model="king")
 
 
+def test_imf_sampler_against_the_lifted_reference_sampler(pkg):
+    """`ic.maschberger_masses` (inverse CDF) pinned to the reference's own rejection sampler
+    (al26_nbody.py:1375-1410), lifted from the reference file when it is mounted: same density function, and what the
+    sampler accepts is p(m) - p(m_upper) -- the inverse-CDF draw thinned accordingly -- by a two-sample KS test, an
+    analytic one-sample KS test, and the thinning's signature at the top end."""
+    from scipy import stats
+    ic = pkg.ic
+    m_lo, m_hi = 0.01, 150.0
+    g_lo, g_hi = ic._maschberger_aux(m_lo), ic._maschberger_aux(m_hi)
+    p_hi = ic.maschberger_pdf(m_hi)
+    # analytic CDF of the accepted density q(m) = (p(m) - p_hi) / (1 - p_hi (m_hi - m_lo))
+    cdf = lambda m: (((ic._maschberger_aux(m) - g_lo) / (g_hi - g_lo)) - p_hi * (m - m_lo)) / (1.0 - p_hi * (m_hi - m_lo))
+    mine = ic.maschberger_masses(400000, np.random.default_rng(7), require_massive=False)
+    assert stats.kstest(mine, cdf).pvalue > 1e-3
+    # the thinning is visible where it matters: stars above 100 Msun are ~45 % rarer than pure Maschberger would make them
+    pure = ic.maschberger_masses(4_000_000, np.random.default_rng(8), require_massive=False, as_reference=False)
+    thinned = ic.maschberger_masses(4_000_000, np.random.default_rng(8), require_massive=False)
+    ratio = np.sum(thinned > 100.0) / np.sum(pure > 100.0)
+    grid = np.linspace(100.0, 150.0, 20001)
+    pm = ic.maschberger_pdf(grid)
+    want = np.sum(pm - p_hi) / np.sum(pm)
+    assert 0.35 < want < 0.6 and ratio == pytest.approx(want, abs=0.12)
+    assert np.array_equal(pure[:1000] == thinned[:1000], np.ones(1000, bool)) or np.mean(pure == thinned) > 0.999  # same parent stream
+    lift = pytest.importorskip("oracle.lift_reference")
+    if not lift.available():
+        pytest.skip("reference file not mounted")
+    ref = lift.lift(names=("maschberger", "gen_mass_numba"))
+    mg = 10.0 ** np.linspace(-2, np.log10(150.0), 200)
+    ref_pdf = np.array([ref["maschberger"](float(v), g_lo, g_hi) for v in mg])
+    assert np.max(np.abs(ref_pdf / ic.maschberger_pdf(mg) - 1.0)) < 1e-13
+    theirs = ref["gen_mass_numba"](g_lo, g_hi, p_hi, ic.maschberger_pdf(m_lo), m_lo, m_hi, 30000)
+    assert stats.ks_2samp(theirs, mine[:200000]).pvalue > 1e-4
+    assert stats.kstest(theirs, cdf).pvalue > 1e-4
+
+
 def test_decay_fractions_literal(pkg):
     from oracle import enrich_oracle as eo
     f26, f60 = pkg.decay_fractions(0.01)

@@ -101,3 +101,40 @@ def test_outer_loop_matches_oracle_loop(pkg, model, n):
         assert set(hist[0]["timings"]) >= {"grav", "stel", "discs", "step"}
     finally:
         gravity.stop()
+
+
+def test_checkpoint_resume_continues_the_run(pkg, tmp_path):
+    """`-r base -nc k` (al26_nbody.py:1641-1656, :1734-1737): a run resumed from its second checkpoint goes on as the
+    uninterrupted run did.  The reference's checkpoint holds no forces or timesteps -- the resumed worker starts cold --
+    so the uninterrupted run is driven with the re-initialisation policy that does the same at every outer step (1);
+    what is left between the two is one ulp in the unit round trip of the checkpointed positions."""
+    U = pkg.units
+    base = str(tmp_path / "run")
+    kw = dict(nstars=600, t_f=10.0 | U.Myr, model="plummer", seed=3, reinit_policy=1)
+    stub = lambda: pkg.StellarStub(lifetime_factor=0.004)
+    cl_a, grav_a, _, enr_a, hist_a = pkg.driver.run(max_outer_steps=14, stellar=stub(), checkpoint_base=base, **kw)
+    try:
+        inv_a, fin_a, alive_a, kicked_a = enr_a.get()
+        x_a = np.stack([grav_a.particles.x.value_in(U.pc), grav_a.particles.vx.value_in(U.kms)])
+        t_a = grav_a.model_time.value_in(U.Myr)
+    finally:
+        grav_a.stop()
+    assert pkg.checkpoint.most_recent_checkpoint(base) == 2          # written after outer steps 1 and 11, plus #0 at start
+    cl_b, grav_b, _, enr_b, hist_b = pkg.driver.run(max_outer_steps=3, stellar=stub(), reload=base, n_checkpoint=2, **kw)
+    try:
+        assert hist_b[0]["t_new_myr"] == pytest.approx(0.12, rel=1e-12)  # the clocks were set from the metadata (:1736)
+        assert [h["sn_events"] for h in hist_b] == [h["sn_events"] for h in hist_a[11:14]]
+        assert sum(len(h["sn_events"]) for h in hist_a) >= 1
+        inv_b, fin_b, alive_b, kicked_b = enr_b.get()
+        assert np.array_equal(alive_a, alive_b) and np.array_equal(kicked_a, kicked_b)
+        scale = np.max(np.abs(inv_a), axis=1, keepdims=True) + 1e-300
+        assert np.max(np.abs(inv_a - inv_b) / scale) < 1e-9 and np.max(np.abs(fin_a - fin_b) / scale) < 1e-9
+        assert np.any(inv_a[pkg.ROW["global26"]] > 0)
+        x_b = np.stack([grav_b.particles.x.value_in(U.pc), grav_b.particles.vx.value_in(U.kms)])
+        assert np.max(np.abs(x_a - x_b)) < 1e-9 * np.max(np.abs(x_a))
+        assert grav_b.model_time.value_in(U.Myr) == pytest.approx(t_a, rel=1e-13)
+        # the yields book went on in the same CSV: header + one row per save step of both runs
+        rows = open(base + "-cluster-yields.csv").read().strip().split("\n")
+        assert rows[0].startswith("time,local_26al") and len(rows) == 1 + 3 + 1
+    finally:
+        grav_b.stop()

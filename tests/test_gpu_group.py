@@ -20,7 +20,7 @@ def _workers(pkg):
 def test_number_of_workers_gravity_surface(pkg):
     k = _workers(pkg)
     U = pkg.units
-    n = 4096
+    n = 4099  # not a multiple of the GPU count: ownership is i % k
     c = pkg.ic.cluster(n, seed=11)
     cv = U.nbody_to_si(1.0 | U.pc, float(c["m_msun"].sum()) | U.MSun)
     cl = pkg.Particles(n)
@@ -58,7 +58,7 @@ def test_number_of_workers_gravity_surface(pkg):
 
 def test_group_enrichment_is_bit_equal_to_one_gpu(pkg):
     k = _workers(pkg)
-    n = 8192
+    n = 8191
     c = pkg.ic.cluster(n, seed=4)
     mass = c["m_msun"]
     hm = np.nonzero(mass >= 13.0)[0]

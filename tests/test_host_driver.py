@@ -98,3 +98,38 @@ def test_yields_book_and_csv_format(pkg, tmp_path):
     z.plate(path)
     assert z.time == y.time and z.sum_local_26al == pytest.approx(y.sum_local_26al) and z.first_write is False
     assert np.allclose(z.local_26al, y.local_26al)
+
+
+def test_checkpoint_round_trip_and_most_recent(pkg, tmp_path):
+    """State checkpoints (al26_nbody.py:347-439): every cluster column, the converter and the metadata come back
+    bit-equal; the newest file of a series is found the way the script finds it (:295-318)."""
+    U = pkg.units
+    ck = pkg.checkpoint
+    cl, cv = pkg.driver.init_cluster("plummer", 300, 1.0 | U.pc, seed=2)
+    cl.mass_26al_local = np.random.default_rng(0).uniform(0, 1e20, 300) | U.kg
+    cl.disk_alive = np.random.default_rng(1).random(300) < 0.5
+    base = str(tmp_path / "sim-test")
+    md = ck.Metadata(t_f=10.0 | U.Myr, model="plummer", nstars=300, cluster_radius=1.0 | U.pc, filename=base)
+    yb = pkg.Yields(base)
+    yb.update_state(0.0 | U.Myr, cl)
+    ck.save_checkpoint(base, 0, cl, cv, yb, md)
+    md.update(0.1 | U.Myr)
+    assert md.most_recent_checkpoint == 1 and md.completion == pytest.approx(0.01)
+    yb.update_state(0.1 | U.Myr, cl)
+    ck.save_checkpoint(base, md.most_recent_checkpoint, cl, cv, yb, md)
+    assert ck.most_recent_checkpoint(base) == 1
+    cl2, cv2, yb2, md2 = ck.load_checkpoint(base, 1)
+    assert set(cl2.attribute_names()) == set(cl.attribute_names()) and np.array_equal(cl2.key, cl.key)
+    for name in cl.attribute_names():
+        a, b = getattr(cl, name), getattr(cl2, name)
+        if hasattr(a, "value_in"):
+            assert a.unit == b.unit and np.array_equal(a.number, b.number), name
+        else:
+            assert np.array_equal(a, b), name
+    assert cv2.length_si == cv.length_si and cv2.time_to_nbody(1.0 | U.Myr) == cv.time_to_nbody(1.0 | U.Myr)
+    assert float(md2.time.value_in(U.Myr)) == 0.1 and md2.most_recent_checkpoint == 1 and md2.filename == base
+    assert yb2.time == yb.time and yb2.sum_local_26al == yb.sum_local_26al
+    with pytest.raises(IOError):
+        ck.most_recent_checkpoint(str(tmp_path / "no-such-run"))
+    with pytest.raises(IOError):
+        ck.load_checkpoint(base, 7)
