@@ -24,6 +24,7 @@ struct StepCtrl {
 };
 
 constexpr int DIST_PROF_N = 12;
+constexpr int BAR_GROUPS = 16;  // sub-counters of the loop kernels' grid barrier
 struct GravHeader {
   double span;  // length of the current evolve call
   double D;     // largest step of the call's dyadic ladder
@@ -49,6 +50,7 @@ struct GravHeader {
   // [6] force on the own share + barrier, [7] corrector + peer stores, [8] cross-GPU barrier, [9] their number,
   // [10] their active particles
   long long dist_prof[DIST_PROF_N];
+  unsigned int bar_sub[BAR_GROUPS][32];  // grid barrier, first level: one 128-byte line per group (zeroed before every launch)
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };

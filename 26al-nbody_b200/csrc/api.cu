@@ -221,8 +221,11 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
 }
 __global__ void k_reset_work(StepCtrl *ctrl) { ctrl->work_counter = 0; }
 __global__ void k_loop_prepare(GravHeader *hdr) {
-  hdr->bar_counter = 0u;
-  hdr->loop_error = 0;
+  if (threadIdx.x < BAR_GROUPS) hdr->bar_sub[threadIdx.x][0] = 0u;
+  if (threadIdx.x == 0) {
+    hdr->bar_counter = 0u;
+    hdr->loop_error = 0;
+  }
 }
 __global__ void k_set_nact(StepCtrl *ctrl, int n_act) {
   ctrl->n_act = n_act;
@@ -424,7 +427,7 @@ bool use_loop(al26_ctx *c) {
 
 // up to max_steps block steps inside one cooperative launch; refreshes the host copy of the header
 int run_loop(al26_ctx *c, int max_steps) {
-  k_loop_prepare<<<1, 1, 0, c->stream>>>(c->g.hdr);
+  k_loop_prepare<<<1, 32, 0, c->stream>>>(c->g.hdr);
   cudaError_t e = cudaSuccess;
   c->launches += 1 + launch_loop(c->g, c->dbg_phase, max_steps, c->stream, &e);
   if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the loop kernel failed: %s", cudaGetErrorString(e));
@@ -438,7 +441,7 @@ int run_loop(al26_ctx *c, int max_steps) {
 // peer-memory mode: up to max_steps block steps (or the single init / sync step) in one cooperative launch
 int run_dist(al26_ctx *c, int mode, int max_steps) {
   if (!c->p2p_ready) return fail(c, AL26_ESTATE, "peer-memory mode: peers' slabs not imported (al26_dist_p2p_import)");
-  k_loop_prepare<<<1, 1, 0, c->stream>>>(c->g.hdr);
+  k_loop_prepare<<<1, 32, 0, c->stream>>>(c->g.hdr);
   cudaError_t e = cudaSuccess;
   c->launches += 1 + launch_loop_dist(c->g, mode, c->dbg_phase, max_steps, c->dist_step, c->stream, &e);
   if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the peer-memory loop kernel failed: %s", cudaGetErrorString(e));

@@ -101,7 +101,7 @@ __device__ __forceinline__ void issue_tile(const GravDev &g, double4 *spos, doub
 // fixed xor-butterfly at the end -> the FP64 pipe time of a tiny block drops by the same factor.
 template <class C, int IPT, bool SPLIT>
 __device__ __forceinline__ void run_item(const GravDev &g, ForceSmemT<C> &sm, const Decomp &d, const int n_act,
-                                         const int item, uint32_t &it) {
+                                         const int item, uint32_t &it, const int *__restrict__ list) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int itile = item / d.n_jsplit, js = item - itile * d.n_jsplit;
   const int j0 = js * d.jchunk;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmemT<C> &sm, co
 #pragma unroll
   for (int q = 0; q < IPT; q++) {
     const int slot = itile * d.ti + q * 32 + isub;
-    const int li = (slot < n_act) ? g.list[slot] : g.list[0];
+    const int li = (slot < n_act) ? list[slot] : list[0];
     const double4 p = g.jpos[g.i0 + li];
     const double4 v = g.jvel[g.i0 + li];
     xi[q] = p.x; yi[q] = p.y; zi[q] = p.z;
@@ -201,7 +201,8 @@ __device__ __forceinline__ void run_item(const GravDev &g, ForceSmemT<C> &sm, co
 // the item loop of one force evaluation: items handed out by the atomic work counter of `ctl`
 template <class C>
 __device__ __forceinline__ void force_items(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *ctl, const int n_act,
-                                            const int n_ctas, uint32_t &it) {
+                                            const int n_ctas, uint32_t &it, const int *__restrict__ list = nullptr) {
+  if (!list) list = g.list;  // the peer-memory loop passes the list of the particles this rank owns instead
   const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, C::IPT, g.big_nact);
   const int n_items = d.n_itiles * d.n_jsplit;
   const int tid = threadIdx.x;
@@ -210,9 +211,9 @@ __device__ __forceinline__ void force_items(const GravDev &g, ForceSmemT<C> &sm,
   // round -- pay no atomic round trip at all.
   int item = blockIdx.x;
   while (item < n_items) {
-    if (d.ipt > 1) run_item<C, C::IPT, false>(g, sm, d, n_act, item, it);
-    else if (n_act <= FORCE_SPLIT_MAX_NACT) run_item<C, 1, true>(g, sm, d, n_act, item, it);
-    else run_item<C, 1, false>(g, sm, d, n_act, item, it);
+    if (d.ipt > 1) run_item<C, C::IPT, false>(g, sm, d, n_act, item, it, list);
+    else if (n_act <= FORCE_SPLIT_MAX_NACT) run_item<C, 1, true>(g, sm, d, n_act, item, it, list);
+    else run_item<C, 1, false>(g, sm, d, n_act, item, it, list);
     if (n_items <= n_ctas) break;
     __syncthreads();
     if (tid == 0) sm.item = n_ctas + atomicAdd(&ctl->work_counter, 1);

@@ -29,16 +29,44 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
 }
 
 // returns false when the launch must be abandoned (error flag raised by some CTA).
-// Arrival is a release-RED at gpu scope (orders the CTA's earlier writes, made visible to thread 0 by the
-// bar.sync), the spin is a relaxed volatile load, and one acquire fence after the spin (ptxas: CCTL.IVALL +
-// MEMBAR) makes the other CTAs' writes visible to every thread released by the trailing bar.sync.
+// Two-level arrival: the CTAs are dealt over BAR_GROUPS sub-counters (one 128-byte line each, so they sit in different
+// L2 slices), the last arriver of a group -- known from the value its atomic returns -- arrives at the top counter, and
+// everybody spins on the top counter.  Same-address atomics serialise in L2 at a few ns each: ~300 arrivals on one
+// word cost ~1.5 us, 19 per sub-counter plus 16 on the top word a tenth of that, for one more atomic round trip on the
+// critical path.  Ordering: every arrival is an acq_rel RMW at gpu scope (releases the CTA's earlier writes, made
+// visible to thread 0 by the bar.sync; the group's last arriver acquires its group's writes and releases them upwards),
+// the spin is a relaxed volatile load, and one acquire fence after it (ptxas: CCTL.IVALL + MEMBAR) makes all CTAs'
+// writes visible to every thread released by the trailing bar.sync.
+// thread 0 of a CTA: arrive.  Returns the top-counter value to wait for; last_of_grid tells the one CTA that completed
+// the barrier (used by the cross-GPU barrier, which lets that CTA speak for the rank).
+__device__ __forceinline__ unsigned barrier_arrive(GravHeader *hdr, unsigned &target, const unsigned n_ctas, bool *last_of_grid) {
+  const unsigned n_groups = n_ctas < (unsigned)BAR_GROUPS ? n_ctas : (unsigned)BAR_GROUPS;
+  const unsigned grp = blockIdx.x % n_groups;
+  const unsigned gsize = (n_ctas - grp + n_groups - 1) / n_groups;  // CTAs b with b % n_groups == grp
+  const unsigned epoch = target / n_ctas;                           // barriers completed so far in this launch
+  target += n_ctas;
+  const unsigned want = (epoch + 1u) * n_groups;
+  unsigned old;
+  bool last = false;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&hdr->bar_sub[grp][0]) : "memory");
+  if (old == (epoch + 1u) * gsize - 1u) {  // last of the group in this epoch
+    if (last_of_grid) {
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&hdr->bar_counter) : "memory");
+      last = (old == want - 1u);
+    } else {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&hdr->bar_counter) : "memory");
+    }
+  }
+  if (last_of_grid) *last_of_grid = last;
+  return want;
+}
+
 __device__ __forceinline__ bool grid_barrier(GravHeader *hdr, unsigned &target, const unsigned n_ctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += n_ctas;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&hdr->bar_counter) : "memory");
+    const unsigned want = barrier_arrive(hdr, target, n_ctas, nullptr);
     unsigned spins = 0;
-    while (ld_volatile_u32(&hdr->bar_counter) < target) {
+    while (ld_volatile_u32(&hdr->bar_counter) < want) {
       if (++spins > LOOP_SPIN_LIMIT) {
         atomicExch(&hdr->loop_error, 1);
         break;
@@ -204,7 +232,7 @@ __device__ __forceinline__ void fused_correct(const GravDev &g, StepCtrl *nxt, c
 
 // force + correctors of a fused step, then wait for the release counter.  Returns false on error.
 template <class C>
-__device__ __forceinline__ bool fused_step(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *cur, StepCtrl *nxt,
+__device__ __noinline__ bool fused_step(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *cur, StepCtrl *nxt,
                                            const int n_act, const int cnt, const int n_parts, const double tn,
                                            const double Dmax, double (*shr)[7], unsigned long long *sh_word,
                                            const int count_n, unsigned long long &tnext_out) {
@@ -259,7 +287,7 @@ __device__ __forceinline__ bool fused_step(const GravDev &g, ForceSmemT<C> &sm, 
 // FUSE: compile the fused small-step path in.  It is a separate instantiation because the extra live state costs
 // the big-block force loop registers (measured: -3 % on N = 1e5 block steps when compiled in but unused).
 template <class C, bool FUSE>
-__global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const GravDev g, const int phase0, const int max_steps) {
+__global__ void __launch_bounds__(C::THREADS, C::MINB) k_loop(const __grid_constant__ GravDev g, const int phase0, const int max_steps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
   __shared__ unsigned long long sh[C::THREADS / 32];
@@ -370,9 +398,9 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
   if (threadIdx.x == 0) {
     if (did_store) __threadfence_system();
     else __threadfence();
-    target += n_ctas;
-    const unsigned old = atomicAdd(&hdr->bar_counter, 1u);
-    if (old == target - 1u) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
+    bool last_of_rank = false;
+    barrier_arrive(hdr, target, n_ctas, &last_of_rank);
+    if (last_of_rank) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
       __threadfence_system();
       const unsigned long long lm = ld_volatile_u64(&nxt->t_next_bits);
       const unsigned long long w0 = tag | (lm >> 32), w1 = tag | (lm & 0xffffffffull);
@@ -416,7 +444,7 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
 
 template <class C, int MODE, bool FUSE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
-    k_loop_dist(const GravDev g, const int phase0, const int max_steps, const unsigned long long xid0) {
+    k_loop_dist(const __grid_constant__ GravDev g, const int phase0, const int max_steps, const unsigned long long xid0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
   __shared__ unsigned long long sh[C::THREADS / 32];
@@ -447,8 +475,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   bool prev_exch = (MODE == MODE_STEP) && g.hdr->dist_prev_exch != 0;
   // the next block time: written by k_begin (identical on every rank) or by the previous launch
   unsigned long long tnext_bits = __ldcg(&g.ctrl[phase0].t_next_bits);
-  GravDev gown = g;
-  gown.list = g.list_own;
   for (int step = 0; step < max_steps; step++) {
     StepCtrl *cur = &g.ctrl[ph];
     StepCtrl *nxt = &g.ctrl[(ph + 1) % 3];
@@ -506,10 +532,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     } else {
       // ---- exchanged step: own share, peer stores, cross-GPU barrier ----
       const unsigned long long this_id = xid + 1;
-      if (n_own > 0) force_items<C>(gown, sm, cur, n_own, n_ctas, it);
+      if (n_own > 0) force_items<C>(g, sm, cur, n_own, n_ctas, it, g.list_own);
       if (!grid_barrier(g.hdr, target, n_ctas)) break;
       TP_STAMP(2);
-      if (n_own > 0) phase_correct<MODE, true>(gown, nxt, n_own, tn, blockIdx.x, n_ctas, sh, shr, this_id);
+      if (n_own > 0) phase_correct<MODE, true>(g, nxt, n_own, tn, blockIdx.x, n_ctas, sh, shr, this_id, -1, g.list_own);
       const bool did_store = n_own > 0 && (int)blockIdx.x < n_own;  // superset of the CTAs that corrected a slot
       TP_STAMP(3);
       if (!dist_barrier(g, target, n_ctas, this_id, nxt, did_store, &sh_tmin, tnext_bits)) break;

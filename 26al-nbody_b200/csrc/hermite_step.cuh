@@ -137,7 +137,7 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
 // buffers' capacity), and every active particle's predicted state + old force go to the compact record g.act, so
 // a small block step needs neither the TMA pipeline nor dependent loads through the list.
 template <bool DIST>
-__device__ __forceinline__ void phase_scan_chunk(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
+__device__ __noinline__ void phase_scan_chunk(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
                                                  const int j0, const int cnt, double4 *sp, double4 *sv,
                                                  unsigned long long *sh, const unsigned long long pull_tag = 0) {
   unsigned long long c_min = INF_BITS;
@@ -333,13 +333,14 @@ __device__ __forceinline__ void correct_slot(const GravDev &g, const double tn, 
 // one active slot of the list: raw output, initial timestep, or the corrector on the particle's global records
 template <int MODE, bool DIST>
 __device__ __forceinline__ void apply_slot(const GravDev &g, const double tn, const int slot, const double r[7],
-                                           unsigned long long &c_bits, const unsigned long long step_id) {
+                                           unsigned long long &c_bits, const unsigned long long step_id,
+                                           const int *__restrict__ list) {
   if (MODE == MODE_RAW) {
-    g.raw_a[slot] = make_double4(r[0], r[1], r[2], pot_without_self(r[6], g.jpos[g.i0 + g.list[slot]].w, g.eps2));
+    g.raw_a[slot] = make_double4(r[0], r[1], r[2], pot_without_self(r[6], g.jpos[g.i0 + list[slot]].w, g.eps2));
     g.raw_j[slot] = make_double4(r[3], r[4], r[5], 0.0);
     return;
   }
-  const int i = g.list[slot];
+  const int i = list[slot];
   if (MODE == MODE_INIT) {
     const double a1[3] = {r[0], r[1], r[2]};
     const double j1[3] = {r[3], r[4], r[5]};
@@ -382,7 +383,8 @@ template <int MODE, bool DIST>
 __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, const int n_act, const double tn,
                                               const int block_id, const int n_blocks, unsigned long long *sh,
                                               double (*shr)[7], const unsigned long long step_id = 0,
-                                              const int count_n = -1) {
+                                              const int count_n = -1, const int *__restrict__ list = nullptr) {
+  if (!list) list = g.list;
   const Decomp d = make_decomp(n_act, g.n_tot, g.decomp_tab, g.force_ipt, g.big_nact);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -414,7 +416,7 @@ __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, c
           for (int w = 1; w < wpb; w++) a += shr[w][c];
           r[c] = a;
         }
-        apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id);
+        apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id, list);
       }
     }
   } else {
@@ -431,7 +433,7 @@ __device__ __forceinline__ void phase_correct(const GravDev &g, StepCtrl *nxt, c
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
       }
-      if (lane == 0) apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id);
+      if (lane == 0) apply_slot<MODE, DIST>(g, tn, slot, r, c_bits, step_id, list);
     }
   }
   if (MODE == MODE_STEP) block_min_to(c_bits, &nxt->t_next_bits, sh);

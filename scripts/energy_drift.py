@@ -2,6 +2,7 @@
 reference loop (al26_nbody.py:786,833): E = K + U, dE = (E0 - E)/E exactly as plotting/al26_plot.py:297-299.
 
     python scripts/energy_drift.py --n 1000 --t-myr 1.0 [--cpu]     # --cpu: also run the CPU oracle on the same ICs
+    python scripts/energy_drift.py --n 100000 --t-myr 0.05 --cpu    # N = 1e5: a bounded horizon the CPU can afford (~2.4e12 pairs)
 Prints one JSON line per run (GPU first)."""
 import argparse, importlib, json, os, sys, time
 import numpy as np
@@ -51,6 +52,8 @@ if not args.no_gpu:
     run("b200", g, g.energies)
 if args.cpu:
     from oracle import hermite as H
+    H.prefer_native()
+    H.use_all_cores()
     o = H.HermiteOracle(args.n)
     o.commit(*p)
     run("cpu-oracle x%d" % H.num_threads(), o, o.energies)
