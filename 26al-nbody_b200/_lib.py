@@ -114,6 +114,7 @@ SIGNATURES = {
     "al26_enrich_set_inventories": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     "al26_enrich_set_units": (C.c_int, [_VP, C.c_double, C.c_double]),
     "al26_enrich_set_mode": (C.c_int, [_VP, C.c_int]),
+    "al26_enrich_profile": (C.c_int, [_VP, _PI64]),
     "al26_enrich_step": (C.c_int, [_VP, C.c_int64, _D, _D, _VP] + [C.c_double] * 6 + [C.c_int, _I32, C.c_int64, _PI64]),
     "al26_enrich_interloper": (C.c_int, [_VP, C.c_int64, _D, _D, _D, C.c_int64] + [C.c_double] * 6),
     "al26_enrich_get_agb_raw": (C.c_int, [_VP, C.c_int64, _D]),

@@ -24,7 +24,6 @@ struct StepCtrl {
 };
 
 constexpr int DIST_PROF_N = 12;
-constexpr int BAR_GROUPS = 16;  // sub-counters of the loop kernels' grid barrier
 struct GravHeader {
   double span;  // length of the current evolve call
   double D;     // largest step of the call's dyadic ladder
@@ -50,7 +49,6 @@ struct GravHeader {
   // [6] force on the own share + barrier, [7] corrector + peer stores, [8] cross-GPU barrier, [9] their number,
   // [10] their active particles
   long long dist_prof[DIST_PROF_N];
-  unsigned int bar_sub[BAR_GROUPS][32];  // grid barrier, first level: one 128-byte line per group (zeroed before every launch)
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
@@ -298,6 +296,7 @@ struct EnrichDev {
   double *hm_rows;    // sliced upload: [mdot, x, y, z][ENR_MAX_SOURCES] of the listed massive stars, gathered by the host
   int *cell_start;    // mode 2: [ENR_GRID_CELLS + 1] list starts
   int *cell_items;    // [27 * ENR_MAX_SOURCES] per-cell candidate lists (every source sits in 27 of them)
+  long long *prof;    // [8] diagnostic: SM cycles of the last CTA of k_enrich_sources per phase (al26_enrich_profile)
   int *sn_events;     // [ENR_MAX_SOURCES]
 };
 struct EnrichParams {

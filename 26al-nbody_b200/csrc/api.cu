@@ -221,7 +221,6 @@ __global__ void k_reset_ctrl(StepCtrl *ctrl, GravHeader *hdr, int zero_counters)
 }
 __global__ void k_reset_work(StepCtrl *ctrl) { ctrl->work_counter = 0; }
 __global__ void k_loop_prepare(GravHeader *hdr) {
-  if (threadIdx.x < BAR_GROUPS) hdr->bar_sub[threadIdx.x][0] = 0u;
   if (threadIdx.x == 0) {
     hdr->bar_counter = 0u;
     hdr->loop_error = 0;
@@ -1534,11 +1533,12 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   CU(cudaMalloc(&c->e_glob, 12 * nt * sizeof(double)));
   CU(cudaMalloc(&c->e_loc, 20 * nl * sizeof(double)));  // r_disk, tau, inv[8], fin[8], agb_raw[2]
   CU(cudaMalloc(&c->e_flags, nt + nl));
-  const size_t n_ints = ENR_NCOUNTERS + 29 * (size_t)ENR_MAX_SOURCES + 2 * ((size_t)ENR_GRID_CELLS + 1);
+  const size_t n_ints = ENR_NCOUNTERS + 29 * (size_t)ENR_MAX_SOURCES + ((size_t)ENR_GRID_CELLS + 1);
   CU(cudaMalloc(&c->e_ints, n_ints * sizeof(int)));
   CU(cudaMemsetAsync(c->e_ints, 0, n_ints * sizeof(int), c->stream));
-  CU(cudaMalloc(&c->e_src, 4 * ENR_MAX_SOURCES * sizeof(double4)));
-  CU(cudaMalloc(&c->e_dbl, (5 * (size_t)ENR_MAX_SOURCES + 16) * sizeof(double)));
+  CU(cudaMalloc(&c->e_src, 4 * (size_t)ENR_MAX_SOURCES * sizeof(double4)));
+  CU(cudaMalloc(&c->e_dbl, (5 * (size_t)ENR_MAX_SOURCES + 16 + 8) * sizeof(double)));
+  CU(cudaMemsetAsync(c->e_dbl, 0, (5 * (size_t)ENR_MAX_SOURCES + 16 + 8) * sizeof(double), c->stream));
   EnrichDev &e = c->e;
   e.n_tot = (int)n; e.d0 = (int)d0; e.n_loc = (int)nloc;
   double *G = c->e_glob;
@@ -1557,6 +1557,7 @@ int al26_enrich_commit(al26_ctx *c, int64_t n, const double *r_disk_km, const do
   e.src_a = c->e_src; e.src_b = c->e_src + ENR_MAX_SOURCES; e.src_f = c->e_src + 2 * ENR_MAX_SOURCES;
   e.ev_a = c->e_src + 3 * ENR_MAX_SOURCES;
   e.ev_b = c->e_dbl; e.fsum = c->e_dbl + ENR_MAX_SOURCES; e.hm_rows = c->e_dbl + ENR_MAX_SOURCES + 16;
+  e.prof = reinterpret_cast<long long *>(c->e_dbl + 5 * (size_t)ENR_MAX_SOURCES + 16);
   CU(cudaMemcpyAsync(G + 8 * nt, wr26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(G + 9 * nt, wr60, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(G + 10 * nt, sn26, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1590,6 +1591,16 @@ int al26_enrich_set_units(al26_ctx *c, double km_per_length, double kms_per_spee
   if (!(km_per_length > 0.0) || !(kms_per_speed > 0.0)) return fail(c, AL26_EINVAL, "unit factors must be positive");
   c->km_per_length = km_per_length;
   c->kms_per_speed = kms_per_speed;
+  return 0;
+}
+
+int al26_enrich_profile(al26_ctx *c, int64_t *cycles8) {
+  if (!c || !cycles8) return AL26_EINVAL;
+  if (!c->e_committed) return fail(c, AL26_ESTATE, "enrich_profile before enrich_commit");
+  CU(cudaSetDevice(c->device));
+  long long h[8];
+  CU(cudaMemcpy(h, c->e.prof, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; k++) cycles8[k] = h[k];
   return 0;
 }
 

@@ -61,44 +61,55 @@ __device__ __forceinline__ void star_vel(const EnrichDev &e, int i, double &x, d
   }
 }
 
-// fixed-order block sum (warp butterflies, then warp 0 over the warp totals in order); result valid in every thread
-__device__ __forceinline__ double block_sum_all(double v, double *sh) {
+// fixed-order block reduction of NV values at once (warp butterflies, then every thread sums / mins the warp rows in
+// order): two barriers for the lot; result valid in every thread.  OP 0: sum, 1: min.
+template <int NV, int OP>
+__device__ __forceinline__ void block_reduce_all(double (&v)[NV], double (*sh)[NV]) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int q = 0; q < NV; q++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(0xffffffffu, v[q], o);
+      v[q] = OP == 0 ? v[q] + w : fmin(v[q], w);
+    }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  double r = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
-  return r;
-}
-__device__ __forceinline__ double block_min_all(double v, double *sh) {
+  if (lane == 0) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < NV; q++) sh[warp][q] = v[q];
+  }
   __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  double r = sh[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmin(r, sh[w]);
-  return r;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double r = sh[0][q];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = OP == 0 ? r + sh[w][q] : fmin(r, sh[w][q]);
+    v[q] = r;
+  }
 }
 
 // phase 0: classify + tables; phase 1: classify + sort only (the host then gathers the massive stars' rows);
 // phase 2: tables only, from the compact per-source rows e.hm_rows = [mdot, x, y, z][ENR_MAX_SOURCES]
 __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, const EnrichParams p, const int phase) {
   __shared__ int keys[ENR_MAX_SOURCES];
-  __shared__ double shd[SRC_T / 32];
+  __shared__ double shd[SRC_T / 32][6];
   __shared__ int shi[SRC_T / 32 + 1];
   __shared__ int is_last;
   pdl_launch_dependents();  // the disc kernel may start its (source-independent) loads
   const int tid = threadIdx.x;
   if (phase != 2) {
-    for (int i = blockIdx.x * SRC_T + tid; i < e.n_tot; i += gridDim.x * SRC_T) {
-      if (e.mass_msun[i] >= 13.0) {
-        const int q = atomicAdd(&e.counters[0], 1);
-        if (q < ENR_MAX_SOURCES) e.hm_list[q] = i;
+    // every mass once; four independent loads in flight per thread (the pass is one memory round trip, not four)
+    const int span = gridDim.x * SRC_T;
+    for (int i0 = blockIdx.x * SRC_T + tid; i0 < e.n_tot; i0 += 4 * span) {
+      double mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) mv[u] = (i0 + u * span < e.n_tot) ? e.mass_msun[i0 + u * span] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (mv[u] >= 13.0) {
+          const int q = atomicAdd(&e.counters[0], 1);
+          if (q < ENR_MAX_SOURCES) e.hm_list[q] = i0 + u * span;
+        }
       }
     }
     __syncthreads();
@@ -109,6 +120,13 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+  }
+  long long tk = clock64();
+#define SRC_PROF(k)                                   \
+  if (tid == 0) {                                     \
+    const long long now = clock64();                  \
+    e.prof[k] = now - tk;                             \
+    tk = now;                                         \
   }
   const int n_raw = (phase == 2) ? e.counters[3] : *(volatile int *)&e.counters[0];
   if (n_raw > ENR_MAX_SOURCES) {  // capacity exceeded: raise the flag, mutate nothing
@@ -121,24 +139,41 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
   }
   const int n_hm = n_raw;
   if (phase != 2) {
-    int np2 = 1;
-    while (np2 < n_hm) np2 <<= 1;
-    for (int k = tid; k < np2; k += SRC_T) keys[k] = (k < n_hm) ? __ldcg(&e.hm_list[k]) : 0x7fffffff;
-    __syncthreads();
-    for (int size = 2; size <= np2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int k = tid; k < np2; k += SRC_T) {
-          const int partner = k ^ stride;
-          if (partner > k) {
-            const bool up = ((k & size) == 0);
-            const int a = keys[k], b = keys[partner];
-            if ((a > b) == up) {
-              keys[k] = b;
-              keys[partner] = a;
+    if (n_hm <= 256) {
+      // rank sort: the keys are distinct star indices; one barrier instead of the bitonic network's log^2 n
+      int *raw = keys + ENR_MAX_SOURCES / 2;
+      int key = 0;
+      if (tid < n_hm) {
+        key = __ldcg(&e.hm_list[tid]);
+        raw[tid] = key;
+      }
+      __syncthreads();
+      if (tid < n_hm) {
+        int rank = 0;
+        for (int j = 0; j < n_hm; j++) rank += (raw[j] < key) ? 1 : 0;
+        keys[rank] = key;
+      }
+      __syncthreads();
+    } else {
+      int np2 = 1;
+      while (np2 < n_hm) np2 <<= 1;
+      for (int k = tid; k < np2; k += SRC_T) keys[k] = (k < n_hm) ? __ldcg(&e.hm_list[k]) : 0x7fffffff;
+      __syncthreads();
+      for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int k = tid; k < np2; k += SRC_T) {
+            const int partner = k ^ stride;
+            if (partner > k) {
+              const bool up = ((k & size) == 0);
+              const int a = keys[k], b = keys[partner];
+              if ((a > b) == up) {
+                keys[k] = b;
+                keys[partner] = a;
+              }
             }
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
     }
     for (int k = tid; k < n_hm; k += SRC_T) e.hm_list[k] = keys[k];
@@ -148,8 +183,10 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
     for (int k = tid; k < n_hm; k += SRC_T) keys[k] = e.hm_list[k];
     __syncthreads();
   }
+  SRC_PROF(0)
 
-  // ---- source table; origin of the fast test = the first source (keeps |x'| at cluster scale) ----
+  // ---- source table, hoisted sums, bounding box, ordered SN event list -- one pass; origin of the fast test = the
+  // first source (keeps |x'| at cluster scale) ----
   double ox = 0.0, oy = 0.0, oz = 0.0;
   if (n_hm > 0) {
     if (phase == 2) {
@@ -158,72 +195,79 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
       star_pos(e, keys[0], ox, oy, oz);
     }
   }
-  double s26 = 0.0, s60 = 0.0;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int k = tid; k < n_hm; k += SRC_T) {
-    const int i = keys[k];
-    double x, y, z, mdot;
-    if (phase == 2) {
-      mdot = e.hm_rows[k];
-      x = e.hm_rows[1 * ENR_MAX_SOURCES + k]; y = e.hm_rows[2 * ENR_MAX_SOURCES + k]; z = e.hm_rows[3 * ENR_MAX_SOURCES + k];
-    } else {
-      star_pos(e, i, x, y, z);
-      mdot = e.mdot[i];
-    }
-    const bool ev = (mdot == 0.0) && (e.kicked[i] == 0);
-    const double c26 = e.wr26[i] * mdot, c60 = e.wr60[i] * mdot;
-    e.src_a[k] = make_double4(x, y, z, c26);
-    e.src_b[k] = make_double4(c60, ev ? e.sn26[i] : 0.0, ev ? e.sn60[i] : 0.0, ev ? 1.0 : 0.0);
-    const double xs = x - ox, ys = y - oy, zs = z - oz;
-    e.src_f[k] = make_double4(-2.0 * xs, -2.0 * ys, -2.0 * zs, (xs * xs + ys * ys + zs * zs) - p.q_local);
-    s26 += c26;
-    s60 += c60;
-    lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z);
-    hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
-  }
-  s26 = block_sum_all(s26, shd);
-  s60 = block_sum_all(s60, shd);
-  __syncthreads();  // src_b is complete (block_sum_all's barriers) -- the event scan below reads it back
-
-  // ---- ordered SN event list (ascending index), kicked, event table ----
-  int base = 0;
+  double sums[2] = {0.0, 0.0};
+  double box[6] = {1e300, 1e300, 1e300, 1e300, 1e300, 1e300};  // min x, y, z, min -x, -y, -z
+  int ev_base = 0;
   for (int k0 = 0; k0 < n_hm; k0 += SRC_T) {
     const int k = k0 + tid;
-    const bool ev = (k < n_hm) && (e.src_b[k].w != 0.0);
+    bool ev = false;
+    double x = 0, y = 0, z = 0, y26 = 0, y60 = 0;
+    int i = 0;
+    if (k < n_hm) {
+      i = keys[k];
+      double mdot;
+      if (phase == 2) {
+        mdot = e.hm_rows[k];
+        x = e.hm_rows[1 * ENR_MAX_SOURCES + k]; y = e.hm_rows[2 * ENR_MAX_SOURCES + k]; z = e.hm_rows[3 * ENR_MAX_SOURCES + k];
+      } else {
+        star_pos(e, i, x, y, z);
+        mdot = e.mdot[i];
+      }
+      ev = (mdot == 0.0) && (e.kicked[i] == 0);
+      const double c26 = e.wr26[i] * mdot, c60 = e.wr60[i] * mdot;
+      const double q26 = e.sn26[i], q60 = e.sn60[i];  // unconditional: one round trip with the loads above
+      y26 = ev ? q26 : 0.0;
+      y60 = ev ? q60 : 0.0;
+      e.src_a[k] = make_double4(x, y, z, c26);
+      e.src_b[k] = make_double4(c60, y26, y60, ev ? 1.0 : 0.0);
+      const double xs = x - ox, ys = y - oy, zs = z - oz;
+      e.src_f[k] = make_double4(-2.0 * xs, -2.0 * ys, -2.0 * zs, (xs * xs + ys * ys + zs * zs) - p.q_local);
+      sums[0] += c26;
+      sums[1] += c60;
+      box[0] = fmin(box[0], x); box[1] = fmin(box[1], y); box[2] = fmin(box[2], z);
+      box[3] = fmin(box[3], -x); box[4] = fmin(box[4], -y); box[5] = fmin(box[5], -z);
+    }
+    // ordered compaction of this tile's events
     const unsigned m = __ballot_sync(0xffffffffu, ev);
     const int lane = tid & 31, warp = tid >> 5;
     if (lane == 0) shi[warp] = __popc(m);
     __syncthreads();
-    int off = base;
-    for (int w = 0; w < warp; w++) off += shi[w];
+    int off = ev_base, tot = 0;
+    for (int w = 0; w < SRC_T / 32; w++) {
+      if (w < warp) off += shi[w];
+      tot += shi[w];
+    }
     if (ev) {
       const int slot = off + __popc(m & ((1u << lane) - 1u));
-      const int i = keys[k];
       e.sn_events[slot] = i;
       e.kicked[i] = 1;
-      const double4 A = e.src_a[k], B = e.src_b[k];
-      e.ev_a[slot] = make_double4(A.x, A.y, A.z, B.y);
-      e.ev_b[slot] = B.z;
+      e.ev_a[slot] = make_double4(x, y, z, y26);
+      e.ev_b[slot] = y60;
     }
-    int tot = 0;
-    for (int w = 0; w < SRC_T / 32; w++) tot += shi[w];
-    base += tot;
+    ev_base += tot;
     __syncthreads();
   }
+  {
+    double (*sh2)[2] = reinterpret_cast<double (*)[2]>(&shd[0][0]);
+    block_reduce_all<2, 0>(sums, sh2);
+  }
   if (tid == 0) {
-    e.counters[1] = base;
-    e.fsum[0] = s26; e.fsum[1] = s60;
+    e.counters[1] = ev_base;
+    e.fsum[0] = sums[0]; e.fsum[1] = sums[1];
     e.fsum[2] = ox; e.fsum[3] = oy; e.fsum[4] = oz;
   }
+  SRC_PROF(1)
   if (p.mode != 2 || n_hm < ENR_PRUNE_MIN_SOURCES) return;  // few sources: the disc kernel scans them all (counters[8] stays 0)
 
   // ---- mode 2: per-cell candidate lists.  A uniform grid over the sources' bounding box plus a one-cell apron, cell
-  // size h >= the local bubble radius; every source is entered into the lists of its 27 neighbouring cells, so a
-  // disc needs ONE lookup -- the list of its own cell holds every source that can be within R of it. ----
-  for (int c = 0; c < 3; c++) {
-    lo[c] = block_min_all(lo[c], shd);
-    hi[c] = -block_min_all(-hi[c], shd);
-  }
+  // size h >= the local bubble radius; every source is entered into the lists of its 27 neighbouring cells, so a disc
+  // needs ONE lookup: the list of its own cell holds every source that can be within R of it.  (Measured and rejected:
+  // lists of {x, y, z, source} records instead of source numbers -- one dependent load fewer per candidate, but the
+  // single table-building CTA then scatters 27 x 32 bytes per source, 39 us at 1000 sources.) ----
+  __syncthreads();
+  block_reduce_all<6, 1>(box, shd);
+  double lo[3] = {box[0], box[1], box[2]};
+  const double hi[3] = {-box[3], -box[4], -box[5]};
   int gd[3];
   double h = p.r_local * (1.0 + 1e-6);
   {
@@ -242,6 +286,7 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
   extern __shared__ int cells[];  // [ncell + 1]
   for (int c = tid; c <= ncell; c += SRC_T) cells[c] = 0;
   __syncthreads();
+  SRC_PROF(2)
   for (int pass = 0; pass < 2; pass++) {
     for (int k = tid; k < n_hm; k += SRC_T) {
       const double4 A = e.src_a[k];
@@ -257,6 +302,7 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
     }
     __syncthreads();
     if (pass == 1) break;
+    SRC_PROF(3)
     {  // inclusive scan of cells[1..ncell] in place (each thread a contiguous run, then the block's run totals)
       const int per = (ncell + SRC_T - 1) / SRC_T;
       const int b = 1 + tid * per, en = min(ncell + 1, b + per);
@@ -281,12 +327,15 @@ __global__ void __launch_bounds__(SRC_T) k_enrich_sources(const EnrichDev e, con
     __syncthreads();
     for (int c = tid; c <= ncell; c += SRC_T) e.cell_start[c] = cells[c];  // the scatter below turns cells[] into cursors
     __syncthreads();
+    SRC_PROF(4)
   }
+  SRC_PROF(5)
   if (tid == 0) {
     e.counters[5] = gd[0]; e.counters[6] = gd[1]; e.counters[7] = gd[2];
     e.counters[8] = 1;  // the lists are there
     e.fsum[5] = lo[0]; e.fsum[6] = lo[1]; e.fsum[7] = lo[2]; e.fsum[8] = inv_h;
   }
+#undef SRC_PROF
 }
 
 // one thread per star.  MODE: see the file header.
@@ -574,7 +623,7 @@ cudaError_t enrich_kernel_setup() {
 
 int enrich_sources_grid(int n_tot, int sm_count) {
   int g = (n_tot + SRC_T - 1) / SRC_T;
-  const int cap = sm_count > 0 ? 2 * sm_count : 296;
+  const int cap = sm_count > 0 ? sm_count : 148;  // 1024 threads x 64 registers: one CTA per SM, one round
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -588,7 +637,7 @@ int launch_enrich_classify(const EnrichDev &e, const EnrichParams &p, int sm_cou
 int launch_enrich(const EnrichDev &e, const EnrichParams &p, int sm_count, bool tables_only, cudaStream_t s, cudaError_t *err) {
   const size_t dsm = (p.mode == 2) ? (size_t)(ENR_GRID_CELLS + 1) * sizeof(int) : 0;  // the cell array of the list build
   if (tables_only) k_enrich_sources<<<1, SRC_T, dsm, s>>>(e, p, 2);
-  else k_enrich_sources<<<enrich_sources_grid(e.n_tot, dsm ? sm_count / 2 : sm_count), SRC_T, dsm, s>>>(e, p, 0);
+  else k_enrich_sources<<<enrich_sources_grid(e.n_tot, sm_count), SRC_T, dsm, s>>>(e, p, 0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((e.n_loc + EN_T - 1) / EN_T);
   cfg.blockDim = dim3(EN_T);

@@ -29,44 +29,20 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
 }
 
 // returns false when the launch must be abandoned (error flag raised by some CTA).
-// Two-level arrival: the CTAs are dealt over BAR_GROUPS sub-counters (one 128-byte line each, so they sit in different
-// L2 slices), the last arriver of a group -- known from the value its atomic returns -- arrives at the top counter, and
-// everybody spins on the top counter.  Same-address atomics serialise in L2 at a few ns each: ~300 arrivals on one
-// word cost ~1.5 us, 19 per sub-counter plus 16 on the top word a tenth of that, for one more atomic round trip on the
-// critical path.  Ordering: every arrival is an acq_rel RMW at gpu scope (releases the CTA's earlier writes, made
-// visible to thread 0 by the bar.sync; the group's last arriver acquires its group's writes and releases them upwards),
-// the spin is a relaxed volatile load, and one acquire fence after it (ptxas: CCTL.IVALL + MEMBAR) makes all CTAs'
-// writes visible to every thread released by the trailing bar.sync.
-// thread 0 of a CTA: arrive.  Returns the top-counter value to wait for; last_of_grid tells the one CTA that completed
-// the barrier (used by the cross-GPU barrier, which lets that CTA speak for the rank).
-__device__ __forceinline__ unsigned barrier_arrive(GravHeader *hdr, unsigned &target, const unsigned n_ctas, bool *last_of_grid) {
-  const unsigned n_groups = n_ctas < (unsigned)BAR_GROUPS ? n_ctas : (unsigned)BAR_GROUPS;
-  const unsigned grp = blockIdx.x % n_groups;
-  const unsigned gsize = (n_ctas - grp + n_groups - 1) / n_groups;  // CTAs b with b % n_groups == grp
-  const unsigned epoch = target / n_ctas;                           // barriers completed so far in this launch
-  target += n_ctas;
-  const unsigned want = (epoch + 1u) * n_groups;
-  unsigned old;
-  bool last = false;
-  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&hdr->bar_sub[grp][0]) : "memory");
-  if (old == (epoch + 1u) * gsize - 1u) {  // last of the group in this epoch
-    if (last_of_grid) {
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&hdr->bar_counter) : "memory");
-      last = (old == want - 1u);
-    } else {
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&hdr->bar_counter) : "memory");
-    }
-  }
-  if (last_of_grid) *last_of_grid = last;
-  return want;
-}
-
+// Arrival is a release-RED at gpu scope on ONE counter (orders the CTA's earlier writes, made visible to thread 0 by the
+// bar.sync), the spin is a relaxed volatile load, and one acquire fence after the spin (ptxas: CCTL.IVALL + MEMBAR)
+// makes the other CTAs' writes visible to every thread released by the trailing bar.sync.
+// Measured and rejected (round 2): a two-level arrival (16 sub-counters, the last arriver of a group -- found from the
+// value its atomic returns -- arrives at the top word).  The CTAs do not arrive at once, so the ~300 same-address REDs
+// are absorbed as they come and what the step waits for is the latency behind the LAST arrival; the extra atomic round
+// trip put 0.7 us on every barrier (N = 1e5, one GPU: 134.4 -> 136.2 us per block step).
 __device__ __forceinline__ bool grid_barrier(GravHeader *hdr, unsigned &target, const unsigned n_ctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned want = barrier_arrive(hdr, target, n_ctas, nullptr);
+    target += n_ctas;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&hdr->bar_counter) : "memory");
     unsigned spins = 0;
-    while (ld_volatile_u32(&hdr->bar_counter) < want) {
+    while (ld_volatile_u32(&hdr->bar_counter) < target) {
       if (++spins > LOOP_SPIN_LIMIT) {
         atomicExch(&hdr->loop_error, 1);
         break;
@@ -231,8 +207,13 @@ __device__ __forceinline__ void fused_correct(const GravDev &g, StepCtrl *nxt, c
 }
 
 // force + correctors of a fused step, then wait for the release counter.  Returns false on error.
+#ifdef AL26_NOINLINE_FUSED
+#define AL26_FUSED_INLINE __noinline__
+#else
+#define AL26_FUSED_INLINE __forceinline__
+#endif
 template <class C>
-__device__ __noinline__ bool fused_step(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *cur, StepCtrl *nxt,
+__device__ AL26_FUSED_INLINE bool fused_step(const GravDev &g, ForceSmemT<C> &sm, StepCtrl *cur, StepCtrl *nxt,
                                            const int n_act, const int cnt, const int n_parts, const double tn,
                                            const double Dmax, double (*shr)[7], unsigned long long *sh_word,
                                            const int count_n, unsigned long long &tnext_out) {
@@ -398,9 +379,9 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
   if (threadIdx.x == 0) {
     if (did_store) __threadfence_system();
     else __threadfence();
-    bool last_of_rank = false;
-    barrier_arrive(hdr, target, n_ctas, &last_of_rank);
-    if (last_of_rank) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
+    target += n_ctas;
+    const unsigned old = atomicAdd(&hdr->bar_counter, 1u);
+    if (old == target - 1u) {  // last CTA of this rank: all of the rank's stores (local and peer) are fenced
       __threadfence_system();
       const unsigned long long lm = ld_volatile_u64(&nxt->t_next_bits);
       const unsigned long long w0 = tag | (lm >> 32), w1 = tag | (lm & 0xffffffffull);

@@ -136,8 +136,13 @@ __device__ __forceinline__ void phase_predict_list(const GravDev &g, StepCtrl *c
 // [j0, j0 + cnt) whose predicted particles it also keeps in its own shared memory (sp / sv, cnt <= the stage
 // buffers' capacity), and every active particle's predicted state + old force go to the compact record g.act, so
 // a small block step needs neither the TMA pipeline nor dependent loads through the list.
+#ifdef AL26_NOINLINE_SCAN
+#define AL26_SCAN_INLINE __noinline__
+#else
+#define AL26_SCAN_INLINE __forceinline__
+#endif
 template <bool DIST>
-__device__ __noinline__ void phase_scan_chunk(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
+__device__ AL26_SCAN_INLINE void phase_scan_chunk(const GravDev &g, StepCtrl *cur, StepCtrl *nxt, const double tn,
                                                  const int j0, const int cnt, double4 *sp, double4 *sv,
                                                  unsigned long long *sh, const unsigned long long pull_tag = 0) {
   unsigned long long c_min = INF_BITS;

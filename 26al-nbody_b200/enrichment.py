@@ -67,6 +67,12 @@ class EnrichCore:
         mode = {"exact": 0, "fast": 1, "pruned": 2}.get(mode, mode)
         self.ctx.chk(self._f("enrich_set_mode")(self.h, int(mode)))
 
+    def profile(self):
+        """SM cycles of the table-building CTA per phase in the last step (include/al26_b200.h: al26_enrich_profile)"""
+        h = (C.c_int64 * 8)()
+        self.ctx.chk(self.L.al26_enrich_profile(self.h, h))
+        return dict(zip(("sort", "table", "clear", "count", "scan", "scatter"), list(h)[:6]))
+
     def set_units(self, km_per_length, kms_per_speed):
         self.ctx.chk(self._f("enrich_set_units")(self.h, float(km_per_length), float(kms_per_speed)))
 

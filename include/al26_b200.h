@@ -292,6 +292,9 @@ int al26_enrich_set_units(al26_ctx *ctx, double km_per_length, double kms_per_sp
  *   2 fast + pruned: as 1, with the local-bubble candidates taken from a cell grid over the massive stars and tested
  *     in the exact form (local rows bit-identical to mode 0); no pair loop, HBM-bound at any source count. */
 int al26_enrich_set_mode(al26_ctx *ctx, int mode);
+/* diagnostic: SM cycles the table-building CTA of the last al26_enrich_step spent in [0] the sort, [1] the source table +
+ * sums + event list, and (mode 2) [2] clearing the cell array, [3] counting, [4] the scan + start table, [5] the scatter */
+int al26_enrich_profile(al26_ctx *ctx, int64_t *cycles8);
 /* replaces one pass of al26_nbody.py:878-1086 (interloper block excluded):
  *   classify (:1194-1216) on mass_msun; 4x calc_wind_abs (:642-702, :897-938) with local bubble
  *   r_bub_local_km (distance-tested) and global bubble r_bub_global_km (= virial radius, no

@@ -45,6 +45,7 @@ for n_hm in (1000, 190, 16):
         print(json.dumps({"sources": n_hm, "mode": mode, "kernel_ms": ms, "first_ms": ker[0],
                           "disc_updates_per_s": n / (ms * 1e-3), "pairs_per_s": n_hm * float(n_disc) / (ms * 1e-3),
                           "hbm_gbs_210B": n * 210.0 / (ms * 1e-3) / 1e9, "frac_hbm_6547.8": n * 210.0 / (ms * 1e-3) / 1e9 / 6547.8,
-                          "local_hits": int(np.count_nonzero(inv[0])), "max_rel_diff_vs_mode0": diff}), flush=True)
+                          "local_hits": int(np.count_nonzero(inv[0])), "max_rel_diff_vs_mode0": diff,
+                          "table_cta_us": {k: round(v / 1965.0, 2) for k, v in e.profile().items()}}), flush=True)
         e.set_mode(0)
 ctx.close()
