@@ -27,7 +27,8 @@ tm = {k: float(sum(h["timings"][k] for h in hist)) for k in ("grav", "stel", "co
 inv, fin, alive, kicked = enrich.get()
 R = pkg.ROW
 lm = (cluster.mass.value_in(U.MSun) <= 3.0)
-print(json.dumps({"config": cfg, "step_mode": step_mode, "engine_cluster_size": eng_cs, **{k: (str(v) if not isinstance(v, (int, str)) else v) for k, v in kw.items()},
+print(json.dumps({"config": cfg, "step_mode_requested": step_mode, "step_mode_effective": ("graph + cluster engine" if eng_cs else "graph"),
+                  "engine_cluster_size": eng_cs, "engine_block_steps": int(eng_steps), "reinit_policy": 0, **{k: (str(v) if not isinstance(v, (int, str)) else v) for k, v in kw.items()},
                   "outer_steps": len(hist), "t_end_myr": hist[-1]["t_new_myr"], "wall_s": wall, "phase_seconds": tm,
                   "block_steps": int(sum(h["block_steps"] for h in hist)), "pairs": float(sum(h["pairs"] for h in hist)),
                   "sn_events": int(sum(len(h["sn_events"]) for h in hist)), "discs_condensed": int((~alive).sum()),
