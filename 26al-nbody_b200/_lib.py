@@ -101,6 +101,8 @@ SIGNATURES = {
     "al26_set_step_mode": (C.c_int, [_VP, C.c_int]),
     "al26_grav_engine_steps": (C.c_int, [_VP, _PI64, C.POINTER(C.c_int)]),
     "al26_dbg_engine_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "al26_set_chip_max": (C.c_int, [_VP, C.c_int]),
+    "al26_grav_chip_steps": (C.c_int, [_VP, _PI64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "al26_set_fuse_max": (C.c_int, [_VP, C.c_int]),
     "al26_grav_fused_steps": (C.c_int, [_VP, _PI64]),
     "al26_grav_fuse_profile": (C.c_int, [_VP, _PI64]),
@@ -236,6 +238,16 @@ class Context:
         self.chk(self.L.al26_grav_engine_steps(self.h, C.byref(n), C.byref(cs)))
         return n.value, cs.value
 
+    def set_chip_max(self, n_act_max):
+        """largest block the chip engine steps (1..256; -1 = default, 0 = engine off)"""
+        self.chk(self.L.al26_set_chip_max(self.h, int(n_act_max)))
+
+    def chip_steps(self):
+        """(block steps taken by the chip engine since the last commit, its CTAs or 0, its block limit)"""
+        n, nc, mx = C.c_int64(0), C.c_int(0), C.c_int(0)
+        self.chk(self.L.al26_grav_chip_steps(self.h, C.byref(n), C.byref(nc), C.byref(mx)))
+        return n.value, nc.value, mx.value
+
     def set_fuse_max(self, n_act_max):
         """loop kernels: largest block that takes the fused small-step path (0 = off); before commit"""
         self.chk(self.L.al26_set_fuse_max(self.h, int(n_act_max)))
@@ -343,6 +355,16 @@ class Group:
         if not h:
             raise Al26Error(-1, f"rank {r} out of range")
         return _GroupRank(self.L, h)
+
+    def set_chip_max(self, n_act_max):
+        """largest block the chip engine steps (1..256; -1 = default, 0 = engine off)"""
+        self.chk(self.L.al26_set_chip_max(self.h, int(n_act_max)))
+
+    def chip_steps(self):
+        """(block steps taken by the chip engine since the last commit, its CTAs or 0, its block limit)"""
+        n, nc, mx = C.c_int64(0), C.c_int(0), C.c_int(0)
+        self.chk(self.L.al26_grav_chip_steps(self.h, C.byref(n), C.byref(nc), C.byref(mx)))
+        return n.value, nc.value, mx.value
 
     def set_fuse_max(self, n_act_max):
         for r in range(self.n_gpus):

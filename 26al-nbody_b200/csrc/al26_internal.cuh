@@ -49,6 +49,9 @@ struct GravHeader {
   // [6] force on the own share + barrier, [7] corrector + peer stores, [8] cross-GPU barrier, [9] their number,
   // [10] their active particles
   long long dist_prof[DIST_PROF_N];
+  unsigned int chip_seq;  // chip engine: the last step number it used (goes on from launch to launch)
+  int pad4;
+  long long n_chip;       // diagnostic: block steps taken by the chip engine, since the last commit
 };
 
 enum StepMode { MODE_STEP = 0, MODE_INIT = 1, MODE_SYNC = 2, MODE_RAW = 3 };
@@ -132,6 +135,9 @@ struct GravDev {
   int *list_own;   // active particles this rank owns (i % world == rank); `list` holds ALL active ones
   int split_min;   // block steps with fewer active particles are computed redundantly by every rank (no exchange)
   void *slab[MAX_PEERS];  // slab[q]: rank q's staging slab as mapped in this process (slab[rank] = own)
+  // chip engine (hermite_chip.cu): per-CTA mail + flags, CTAs, particles per CTA, largest block it steps (0 = off)
+  void *chip_mail;
+  int chip_n, chip_p, chip_max;
 };
 
 // ---- the cluster engine (hermite_engine.cu): runs of small block steps for small N inside one thread-block cluster
@@ -141,6 +147,22 @@ int engine_smem_bytes(int p_cap);
 bool engine_plan(int n, int max_smem, int *cs_out, int *p_cap_out);
 cudaError_t engine_kernel_setup(int max_smem_optin);
 bool engine_fits(int cs, int p_cap, int max_smem_optin);
+
+// ---- the chip engine (hermite_chip.cu): runs of small block steps with the particle set resident in the shared
+// memory of the whole chip, one CTA per SM; no grid barrier, no atomics: single-writer mail, flags and partial rows
+constexpr int CHIP_CAP = 256;       // largest block the engine can be asked to step (records per CTA)
+constexpr int CHIP_MAX_CTAS = 256;  // CTAs at most
+constexpr int CHIP_MAX_ACT_DEFAULT = 32;
+struct alignas(128) ChipMail {
+  unsigned long long w[4];  // header: three self-validating words {step | hi(min t+dt)}, {step | lo}, {step | count}
+  int idx[CHIP_CAP];        // the particles of this chunk that attain the chunk's minimum ...
+  double4 pp[CHIP_CAP], pv[CHIP_CAP];  // ... predicted to that time
+};
+int chip_smem_bytes(int p_cap);
+size_t chip_mail_bytes(int n_ctas);
+bool chip_plan(int n, int n_ctas, int max_smem, int *p_cap_out);
+cudaError_t chip_kernel_setup(int max_smem_optin);
+bool chip_fits(int n_ctas, int p_cap, int sm_count, int max_smem_optin);
 
 // ---- work decomposition of one force evaluation, a pure function of (n_act, n_tot, grid) so
 // the force kernel and the reduce/corrector kernel agree without communicating ----
@@ -246,6 +268,7 @@ int launch_loop_dist(const GravDev &g, int mode, int phase, int max_steps, unsig
                      cudaStream_t s, cudaError_t *err);
 int launch_pull(const GravDev &g, unsigned long long step_id, cudaStream_t s);
 int launch_engine(const GravDev &g, int phase, int cs, int p_cap, cudaStream_t s, cudaError_t *err);
+int launch_chip(const GravDev &g, int phase, cudaStream_t s, cudaError_t *err);
 cudaError_t loop_kernel_setup();
 int loop_max_ctas_per_sm(int variant);
 

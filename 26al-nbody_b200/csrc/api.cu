@@ -107,12 +107,15 @@ struct al26_ctx {
   int max_rounds = FORCE_MAX_ROUNDS;      // tuning: work items per CTA at most
   int fuse_max = -1;                      // loop kernels: block steps of at most this many particles take the fused path (0 = off, -1 = by N)
   double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
-  int step_mode = -1;     // 1 GPU: -1 = automatic (2 when the particles fit one cluster, else 0), 0 = CUDA graph of 3 kernels per block step, 1 = persistent cooperative loop kernel, 2 = graph + cluster engine
+  int step_mode = -1;     // 1 GPU: -1 = automatic (2 when the particles fit one cluster, else 3 when they fit the chip, else 0), 0 = CUDA graph of 3 kernels per block step, 1 = persistent cooperative loop kernel, 2 = graph + cluster engine, 3 = graph + chip engine
   bool coop_ok = false;   // device supports cooperative launch
   int max_smem_optin = 0;  // largest dynamic shared memory a block may opt in to
   bool engine_ok = false;  // the cluster-engine kernel's attributes could be set
   bool engine_on = false;  // this commit's graph carries the engine (step mode 2 and the particles fit one cluster)
   int engine_cs = 0, engine_p = 0;  // its cluster size and per-CTA particle capacity
+  bool chip_ok = false;    // the chip-engine kernel's attributes could be set
+  bool chip_on = false;    // this commit runs its small block steps in the chip engine (hermite_chip.cu)
+  int chip_max = -1;       // largest block the chip engine steps (-1 = default, 0 = engine off)
   cudaGraphExec_t graph = nullptr;
   int graph_steps = 0;
   bool graph_stale = false;  // parameters changed since the graph captured them by value
@@ -276,7 +279,7 @@ void free_gravity(al26_ctx *c) {
   c->slab = nullptr;
   c->p2p_ready = false;
   void *ptrs[] = {g.pos, g.vel, g.acc, g.jrk, g.t, g.dt, g.jpos, g.jvel, g.list, g.part_a, g.part_j, g.ctrl, g.hdr,
-                  (void *)g.decomp_tab, g.list_own, g.act};
+                  (void *)g.decomp_tab, g.list_own, g.act, g.chip_mail};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   g = GravDev{};
@@ -333,12 +336,43 @@ void decide_engine(al26_ctx *c) {
   c->engine_p = p_cap;
 }
 
+// The chip engine (hermite_chip.cu) for the particle sets that do not fit one cluster: one GPU in step modes -1 / 3
+// (in front of every block step of the graph, like the cluster engine), and the peer-memory multi-GPU mode (between the
+// launches of the loop kernel, which hands every run of small steps over to it).  Decided once per commit.
+void decide_chip(al26_ctx *c) {
+  c->chip_on = false;
+  GravDev &g = c->g;
+  g.chip_max = 0;
+  if (!c->chip_ok || !c->coop_ok || !c->committed || c->chip_max == 0 || g.n_loc != g.n_tot) return;
+  if (c->world == 1 ? (c->step_mode != 3 && c->step_mode != -1) : !is_p2p(c)) return;
+  if (c->world == 1 && c->engine_on) return;  // the cluster engine is the better tool where it fits
+  int p_cap = 0;
+  const int nc = c->sm_count < CHIP_MAX_CTAS ? c->sm_count : CHIP_MAX_CTAS;
+  if (!chip_plan(g.n_tot, nc, c->max_smem_optin, &p_cap) || !chip_fits(nc, p_cap, c->sm_count, c->max_smem_optin)) return;
+  if (!g.chip_mail) {
+    if (cudaMalloc(&g.chip_mail, chip_mail_bytes(nc)) != cudaSuccess) {
+      cudaGetLastError();
+      g.chip_mail = nullptr;
+      return;
+    }
+    cudaMemsetAsync(g.chip_mail, 0, chip_mail_bytes(nc), c->stream);
+  }
+  g.chip_n = nc;
+  g.chip_p = p_cap;
+  g.chip_max = c->chip_max > 0 ? (c->chip_max < CHIP_CAP ? c->chip_max : CHIP_CAP) : CHIP_MAX_ACT_DEFAULT;
+  c->chip_on = true;
+}
+
 // one block step (or the init / sync variant) enqueued on the stream
 int enqueue_step(al26_ctx *c, int mode, int phase, bool with_engine = false) {
   if (with_engine && mode == MODE_STEP && c->engine_on) {  // first every small step up to the next big one, on chip
     cudaError_t e = cudaSuccess;
     c->launches += launch_engine(c->g, phase, c->engine_cs, c->engine_p, c->stream, &e);
     if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cluster-engine launch failed: %s", cudaGetErrorString(e));
+  } else if (with_engine && mode == MODE_STEP && c->chip_on) {
+    cudaError_t e = cudaSuccess;
+    c->launches += launch_chip(c->g, phase, c->stream, &e);
+    if (e != cudaSuccess) return fail(c, AL26_ECUDA, "chip-engine launch failed: %s", cudaGetErrorString(e));
   }
   c->launches += launch_predict_list(c->g, mode, phase, c->stream);
   int rc = gather_j(c);
@@ -357,11 +391,23 @@ constexpr int GRAPH_ROUNDS = 8;  // 3 phases x 8 = 24 block steps per graph laun
 // inside the first slots: a shorter graph leaves fewer no-op launches behind (AL26_GRAPH_ROUNDS_ENGINE overrides)
 constexpr int GRAPH_ROUNDS_ENGINE = 2;
 
+int build_graph_once(al26_ctx *c);
 int build_graph(al26_ctx *c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   c->graph = nullptr;
-  if (is_p2p(c)) return 0;  // the peer-memory path runs entirely inside the loop kernel
   decide_engine(c);
+  decide_chip(c);
+  if (is_p2p(c)) return 0;  // the peer-memory path runs inside the loop kernel (and the chip engine)
+  int rc = build_graph_once(c);
+  if (rc && c->chip_on) {  // a driver that cannot capture the cooperative launch: the plain graph
+    cudaGetLastError();
+    c->chip_on = false;
+    c->g.chip_max = 0;
+    rc = build_graph_once(c);
+  }
+  return rc;
+}
+int build_graph_once(al26_ctx *c) {
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   const int64_t l0 = c->launches;
@@ -451,6 +497,36 @@ int run_dist(al26_ctx *c, int mode, int max_steps) {
   c->dist_step = c->h_hdr->dist_step;
   return 0;
 }
+// peer-memory mode with the chip engine: [k_chip, k_loop_dist] pairs queued back to back -- the chip engine takes every run
+// of small block steps (redundantly on every rank, no traffic), the loop kernel the bigger ones and hands the next run
+// back; phase and exchange id travel through the header, so the host only looks at it once per batch
+int run_dist_chained(al26_ctx *c) {
+  if (!c->p2p_ready) return fail(c, AL26_ESTATE, "peer-memory mode: peers' slabs not imported (al26_dist_p2p_import)");
+  k_loop_prepare<<<1, 32, 0, c->stream>>>(c->g.hdr);
+  c->launches++;
+  int pairs_needed = 0;
+  int batch = c->expected_graph_launches > 8 ? c->expected_graph_launches - 4 : 8;
+  while (true) {
+    for (int b = 0; b < batch; b++) {
+      cudaError_t e = cudaSuccess;
+      c->launches += launch_chip(c->g, -1, c->stream, &e);
+      if (e != cudaSuccess) return fail(c, AL26_ECUDA, "chip-engine launch failed: %s", cudaGetErrorString(e));
+      c->launches += launch_loop_dist(c->g, MODE_STEP, -1, 1 << 30, 0ull, c->stream, &e);
+      if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the peer-memory loop kernel failed: %s", cudaGetErrorString(e));
+      pairs_needed++;
+    }
+    int rc = read_header(c);
+    if (rc) return rc;
+    if (c->h_hdr->loop_error) return fail(c, AL26_ECUDA, "peer-memory loop / chip engine: spin limit hit (code %d)", c->h_hdr->loop_error);
+    if (c->h_hdr->done) break;
+    batch = 8;
+  }
+  c->expected_graph_launches = pairs_needed;
+  c->dbg_phase = c->h_hdr->phase;
+  c->dist_step = c->h_hdr->dist_step;
+  return 0;
+}
+
 // one init or sync step in peer-memory mode, then pull what was staged into the local state
 int dist_single(al26_ctx *c, int mode) {
   reset_ctrl(c, 0);
@@ -569,6 +645,8 @@ al26_ctx *al26_create(int device_id) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
   c->engine_ok = engine_kernel_setup(c->max_smem_optin) == cudaSuccess;
   if (!c->engine_ok) cudaGetLastError();
+  c->chip_ok = chip_kernel_setup(c->max_smem_optin) == cudaSuccess;
+  if (!c->chip_ok) cudaGetLastError();
   return c;
 }
 
@@ -899,7 +977,9 @@ int al26_grav_initialize(al26_ctx *c) {
 // caller, which clears in_evolve (so a CUDA error does not wedge the context in "evolve already in progress")
 static int evolve_run(al26_ctx *c, const int64_t l0, int64_t *n_block_steps, int64_t *n_pairs) {
   int rc;
-  if (is_p2p(c)) {
+  if (is_p2p(c) && c->chip_on) {
+    if ((rc = run_dist_chained(c))) return rc;
+  } else if (is_p2p(c)) {
     while (true) {
       if ((rc = run_dist(c, MODE_STEP, 1 << 30))) return rc;
       if (c->h_hdr->done) break;
@@ -915,7 +995,7 @@ static int evolve_run(al26_ctx *c, const int64_t l0, int64_t *n_block_steps, int
     while (true) {
       for (int b = 0; b < batch; b++) {
         CU(cudaGraphLaunch(c->graph, c->stream));
-        c->launches += (c->engine_on ? 4 : 3) * c->graph_steps;
+        c->launches += (c->engine_on || c->chip_on ? 4 : 3) * c->graph_steps;
         launches_needed++;
       }
       batch = 1;
@@ -1394,11 +1474,32 @@ int al26_grav_fuse_profile(al26_ctx *c, int64_t *ns8) {  // 16 values
 
 int al26_set_step_mode(al26_ctx *c, int mode) {
   if (!c) return AL26_EINVAL;
-  if (mode < -1 || mode > 2)
-    return fail(c, AL26_EINVAL, "step mode must be -1 (automatic), 0 (graph), 1 (persistent loop) or 2 (graph + cluster engine)");
+  if (mode < -1 || mode > 3)
+    return fail(c, AL26_EINVAL, "step mode must be -1 (automatic), 0 (graph), 1 (persistent loop), 2 (graph + cluster engine) or 3 (graph + chip engine)");
   if (c->in_evolve) return fail(c, AL26_ESTATE, "set_step_mode during evolve");
   if (mode != c->step_mode) c->graph_stale = c->committed;  // the graph may gain / lose the engine nodes
   c->step_mode = mode;
+  return 0;
+}
+
+int al26_set_chip_max(al26_ctx *c, int n_act_max) {
+  if (!c) return AL26_EINVAL;
+  if (n_act_max < -1 || n_act_max > CHIP_CAP) return fail(c, AL26_EINVAL, "chip_max must be -1 (default), 0 (off) or 1..%d", CHIP_CAP);
+  if (c->in_evolve) return fail(c, AL26_ESTATE, "set_chip_max during evolve");
+  if (n_act_max != c->chip_max) c->graph_stale = c->committed;
+  c->chip_max = n_act_max;
+  return 0;
+}
+
+int al26_grav_chip_steps(al26_ctx *c, int64_t *n_chip, int *n_ctas, int *n_act_max) {
+  if (!c || !n_chip) return AL26_EINVAL;
+  if (!c->committed) return fail(c, AL26_ESTATE, "chip_steps before commit");
+  CU(cudaSetDevice(c->device));
+  int rc = read_header(c);
+  if (rc) return rc;
+  *n_chip = c->h_hdr->n_chip;
+  if (n_ctas) *n_ctas = c->chip_on ? c->g.chip_n : 0;
+  if (n_act_max) *n_act_max = c->chip_on ? c->g.chip_max : 0;
   return 0;
 }
 

@@ -24,6 +24,7 @@ UNITS = [
     ("hermite_step.cu", ["--fmad=false"]),
     ("hermite_loop.cu", ["--fmad=false"]),
     ("hermite_engine.cu", ["--fmad=false"]),
+    ("hermite_chip.cu", ["--fmad=false"]),
     ("enrich.cu", ["--fmad=false"]),
     ("analysis.cu", ["--fmad=false"]),
     ("api.cu", ["--fmad=false"]),

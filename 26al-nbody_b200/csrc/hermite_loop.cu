@@ -423,9 +423,13 @@ __device__ __forceinline__ bool dist_barrier(const GravDev &g, unsigned &target,
   return ld_volatile_u32((const unsigned *)&hdr->loop_error) == 0;
 }
 
+// phase_arg < 0 (chained with the chip engine, hermite_chip.cu): the StepCtrl phase and the exchange id are taken from
+// the header, where the previous launch left them -- the host queues [k_chip, k_loop_dist] pairs without reading anything
+// back -- and a block step the chip engine can take is handed over to it: the scheduler pass (which has pulled the
+// previous exchange) is abandoned, its list / minimum are cleaned up by k_chip, and the launch ends.
 template <class C, int MODE, bool FUSE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
-    k_loop_dist(const __grid_constant__ GravDev g, const int phase0, const int max_steps, const unsigned long long xid0) {
+    k_loop_dist(const __grid_constant__ GravDev g, const int phase_arg, const int max_steps, const unsigned long long xid_arg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ForceSmemT<C> &sm = *reinterpret_cast<ForceSmemT<C> *>(smem_raw);
   __shared__ unsigned long long sh[C::THREADS / 32];
@@ -444,6 +448,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   force_smem_init<C>(sm);
   uint32_t it = 0;
   unsigned target = 0;
+  const bool chained = (MODE == MODE_STEP) && phase_arg < 0;
+  const int phase0 = chained ? g.hdr->phase : phase_arg;
+  const unsigned long long xid0 = chained ? g.hdr->dist_step : xid_arg;
   int ph = phase0;
   const double span = g.hdr->span;
   const bool fuse = FUSE && (MODE == MODE_STEP) && g.fuse_max > 0;  // fused small steps: redundant, non-exchanged ones only
@@ -487,6 +494,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     const int n_all = __ldcg(&cur->n_act);
     const int n_own = __ldcg(&cur->pad[0]);
     const bool exchange = (MODE != MODE_STEP) || n_all >= g.split_min;
+    if (chained && g.chip_max > 0 && n_all > 0 && n_all <= g.chip_max) {  // uniform: a run of small steps begins
+      prev_exch = false;  // this pass has pulled what the last exchange staged
+      break;
+    }
     if (!exchange && fuse && n_all > 0 && n_all <= g.fuse_max) {
       // ---- redundant AND small: the fused path (one barrier, see above) ----
       if (!fused_step<C>(g, sm, cur, nxt, n_all, CHUNK_CNT, CHUNK_PARTS, tn, g.Dmax, shr, &sh_tmin, n_own, tnext_bits)) break;

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_begin(const GravDev g, const dou
     g.hdr->span = span;
     g.hdr->D = D;
     g.hdr->done = 0;
+    g.hdr->phase = 0;  // the chained peer-memory launches (chip engine + loop kernel) pick the StepCtrl phase up from here
   }
   block_min_to(c, &g.ctrl[0].t_next_bits, sh);
 }

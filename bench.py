@@ -61,7 +61,8 @@ def parse():
     ap.add_argument("--dist-mode", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory exchange or NCCL all-gather")
     ap.add_argument("--split-min", type=int, default=0, help="peer-memory mode: exchange only blocks of at least this many active particles (0 = auto)")
     ap.add_argument("--fuse-max", type=int, default=-1, help="loop kernels: largest block on the fused small-step path (0 = off, -1 = library default)")
-    ap.add_argument("--step-mode", type=int, default=-1, choices=[-1, 0, 1, 2], help="1 GPU: -1 = library default (graph; + cluster engine when N fits one cluster), 0 = CUDA graph, 1 = persistent loop kernel, 2 = graph + cluster engine")
+    ap.add_argument("--step-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3], help="1 GPU: -1 = library default (graph; + cluster engine when N fits one cluster, + chip engine when it fits the chip), 0 = CUDA graph, 1 = persistent loop kernel, 2 = graph + cluster engine, 3 = graph + chip engine")
+    ap.add_argument("--chip-max", type=int, default=-1, help="largest block the chip engine steps (-1 = library default, 0 = engine off)")
     ap.add_argument("--cpu-pairs", type=float, default=1.2e10, help="pair budget of the CPU sample")
     ap.add_argument("--no-config4", action="store_true", help="skip the N=1e6 gravity-only sub-record (BASELINE config 4)")
     ap.add_argument("--config4-dt-myr", type=float, default=5.0e-4, help="outer step of the config-4 evolve (forced full-N sync < 10 %% of its pairs)")
@@ -460,6 +461,7 @@ def main():
     ctx = pkg.Context(local)
     ctx.set_step_mode(args.step_mode)
     ctx.set_fuse_max(args.fuse_max)
+    ctx.set_chip_max(args.chip_max)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pkg.dist.init_context(ctx, rank, world, device="cuda", mode=args.dist_mode, split_min=args.split_min)
@@ -537,6 +539,8 @@ def main():
     k1, u1, _ = g.energies()
     de = ((k0 + u0) - (k1 + u1)) / (k1 + u1)
     value = tot_pairs / (tot_ms * 1e-3)
+    n_chip, chip_ctas, chip_max = ctx.chip_steps()
+    n_eng, eng_cs = ctx.engine_steps()
 
     # ---- end-to-end arm: host buffers in / out every step --------------------------------------
     m_host = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -588,6 +592,8 @@ def main():
                        "l2": "256 MiB device write between timed steps (state is 20 MB < L2; kernel is FP64-bound)"},
             "block_steps_per_step": tot_steps / args.steps, "pairs_per_step": tot_pairs / args.steps,
             "wall_s_timed_region": wall, "dE_over_E": de, "t_end_nbody": t_now,
+            "small_steps": {"chip_engine_ctas": chip_ctas, "chip_engine_max_block": chip_max, "chip_engine_block_steps_since_commit": n_chip,
+                            "cluster_engine_size": eng_cs, "cluster_engine_block_steps_since_commit": n_eng},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches + e_launch), "clocks": clocks}
 
     if not args.no_enrich:

@@ -213,7 +213,7 @@ int al26_set_big_block(al26_ctx *ctx, int n_act_min);
  * applies at the next al26_grav_commit */
 int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_pairs);
 /* tuning hook: how block steps are driven on one GPU.  -1 (default): automatic -- 2 when the particles fit one
- * cluster (N <= ~13000), else 0.  0: a CUDA graph of three kernels per block
+ * cluster (N <= ~13000), else 3 when they fit the chip (N <= ~1.2e5), else 0.  0: a CUDA graph of three kernels per block
  * step, relaunched until the device reports the call done; 1: one persistent cooperative kernel runs the
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).
  * Bit-identical results (except the loop kernel's fused small steps, al26_set_fuse_max: identical integer work,
@@ -234,6 +234,20 @@ int al26_grav_engine_steps(al26_ctx *ctx, int64_t *n_engine, int *cluster_size);
  * max_smem_per_block bytes of shared memory (232448 on B200) -- cluster size (8 or 16; 0 = the particles do not fit),
  * particles per CTA, shared memory per CTA */
 int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *particles_per_cta, int *smem_bytes);
+/* step mode 3 = the graph with the CHIP ENGINE in front of every block step, for the particle sets that do not fit one
+ * cluster (automatic from N ~ 1.3e4 up to ~1.2e5 on B200: 144 + 64 B per particle in the shared memory of 148 SMs):
+ * one CTA per SM keeps a contiguous chunk of the particles resident for a whole run of small block steps; the CTAs
+ * talk through single-writer records in L2 that carry their step number (no grid barrier, no atomics): the chunk's
+ * min(t + dt) with the particles that attain it already predicted, one force partial per (active particle, chunk),
+ * one "partials stored" flag per CTA.  A step is 5-6 dependent L2 hops instead of 10-18 and never passes over the
+ * state in L2.  In the peer-memory multi-GPU mode (al26_dist_set_mode 1) the same kernel takes every run of small block
+ * steps -- which every rank computes redundantly -- between the launches of the loop kernel.  Identical integer work,
+ * positions to rounding.  al26_set_chip_max: largest block the engine steps (1..256; -1 = default 32; 0 = engine
+ * off), before or after commit; al26_grav_chip_steps: block steps it took since the last commit, its CTAs (0 = not in
+ * use) and its block limit (the last two may be NULL).  Stands in, like every step mode, for ph4's evolve loop behind
+ * gravity.evolve_model (al26_nbody.py:833). */
+int al26_set_chip_max(al26_ctx *ctx, int n_act_max);
+int al26_grav_chip_steps(al26_ctx *ctx, int64_t *n_chip, int *n_ctas, int *n_act_max);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
  * else off) take the fused small-step path

@@ -22,10 +22,11 @@ def make(pkg, n, seed, model="plummer"):
     return [c[k] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
 
 
-@pytest.fixture(params=[(1, 32), (1, 0), (0, 32), (2, 32)], ids=["loop-fused", "loop", "graph", "engine"])
+@pytest.fixture(params=[(1, 32), (1, 0), (0, 32), (2, 32), (3, 32)], ids=["loop-fused", "loop", "graph", "engine", "chip"])
 def grav(pkg, ctx, request):
     """The ways of driving block steps: the persistent cooperative loop kernel with and without its fused
-    small-step path, the CUDA graph, and the graph with the cluster engine in front of every block step."""
+    small-step path, the CUDA graph, and the graph with the cluster engine / the chip engine in front of every block
+    step."""
     mode, fuse = request.param
     ctx.set_step_mode(mode)
     ctx.set_fuse_max(fuse)
@@ -307,6 +308,50 @@ def test_cluster_engine_takes_the_small_steps_and_agrees(pkg, ctx, n, model):
     a, b = out[2]["state"], out[0]["state"]
     assert vec_rel(a[1:4], b[1:4]) < 1e-10 and vec_rel(a[4:7], b[4:7]) < 1e-10
     assert abs(out[2]["de"] - out[0]["de"]) < 1e-9 + 1e-3 * abs(out[0]["de"])
+
+
+@pytest.mark.parametrize("n,model,chip_max", [(1000, "plummer", 32), (20000, "plummer", 32), (20000, "fractal", 256),
+                                               (100_000, "plummer", 32), (100_000, "plummer", 200)])
+def test_chip_engine_takes_the_small_steps_and_agrees(pkg, ctx, n, model, chip_max):
+    """Step mode 3: the runs of small block steps are taken by the chip engine (one CTA per SM, the particle set resident
+    in shared memory, single-writer mail instead of grid barriers); identical integer work, trajectory to rounding, same
+    energy error as the plain graph -- and, where the oracle is affordable, the oracle's integer work."""
+    p = make(pkg, n, seed=5, model=model)
+    span = 2.0 ** -7 if n <= 20000 else 2.0 ** -10
+    out = {}
+    try:
+        for mode in (3, 0):
+            ctx.set_step_mode(mode)
+            ctx.set_chip_max(chip_max)
+            g = pkg.GravityCore(ctx=ctx, eps2=1e-6 if model == "fractal" else 0.0)
+            g.set_time(0.0)
+            g.commit(*p)
+            e0 = sum(g.energies()[:2])
+            work = [g.evolve(span * k) for k in range(1, 4)]  # the engine restarts with every call
+            h = ctx.block_histogram()
+            out[mode] = dict(work=work, state=g.get_state(), dt=g.get_timesteps()[1], hist=h, chip=ctx.chip_steps(),
+                             de=(e0 - sum(g.energies()[:2])) / e0)
+    finally:
+        ctx.set_step_mode(-1)
+        ctx.set_chip_max(-1)
+    n_chip, n_ctas, mx = out[3]["chip"]
+    assert n_ctas > 0 and mx == chip_max and out[0]["chip"][:2] == (0, 0)
+    hist = out[3]["hist"]
+    lo = sum(hist[b] for b in range(32) if (2 << b) - 1 <= chip_max)  # bins that lie entirely within the engine's limit
+    hi = sum(hist[b] for b in range(32) if (1 << b) <= chip_max)
+    assert lo <= n_chip <= hi and n_chip > 0
+    assert out[3]["work"] == out[0]["work"] and out[3]["hist"] == out[0]["hist"]
+    assert np.array_equal(out[3]["dt"], out[0]["dt"])
+    a, b = out[3]["state"], out[0]["state"]
+    assert np.array_equal(a[0], b[0])
+    assert vec_rel(a[1:4], b[1:4]) < 1e-10 and vec_rel(a[4:7], b[4:7]) < 1e-10
+    assert abs(out[3]["de"] - out[0]["de"]) < 1e-9 + 1e-3 * abs(out[0]["de"])
+    if n <= 20000 and model == "plummer":
+        o = H.HermiteOracle(n); o.commit(*p)
+        assert [o.evolve(span * k) for k in range(1, 4)] == out[3]["work"]
+        assert np.array_equal(o.get_timesteps()[1], out[3]["dt"])
+        os_ = o.get_state()
+        assert vec_rel(a[1:4], os_[1:4]) < 1e-10 and vec_rel(a[4:7], os_[4:7]) < 1e-10
 
 
 def test_set_mass_and_time_setter(pkg, grav):
