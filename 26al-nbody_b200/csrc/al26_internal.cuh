@@ -154,9 +154,9 @@ constexpr int CHIP_CAP = 256;       // largest block the engine can be asked to 
 constexpr int CHIP_MAX_CTAS = 256;  // CTAs at most
 constexpr int CHIP_MAX_ACT_DEFAULT = 32;
 struct alignas(128) ChipMail {
-  unsigned long long w[4];  // header: three self-validating words {step | hi(min t+dt)}, {step | lo}, {step | count}
-  int idx[CHIP_CAP];        // the particles of this chunk that attain the chunk's minimum ...
-  double4 pp[CHIP_CAP], pv[CHIP_CAP];  // ... predicted to that time
+  unsigned long long w[16];            // header: {step | hi(min t+dt)}, {step | lo}, {step | count}; the rest pads to a line
+  unsigned long long rec[CHIP_CAP][16];  // the particles of this chunk that attain the chunk's minimum, predicted to that time:
+                                         // {step | half} words: x, y, z, m, vx, vy, vz as {hi, lo} pairs, then the index
 };
 int chip_smem_bytes(int p_cap);
 size_t chip_mail_bytes(int n_ctas);

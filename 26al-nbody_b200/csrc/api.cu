@@ -107,7 +107,7 @@ struct al26_ctx {
   int max_rounds = FORCE_MAX_ROUNDS;      // tuning: work items per CTA at most
   int fuse_max = -1;                      // loop kernels: block steps of at most this many particles take the fused path (0 = off, -1 = by N)
   double item_overhead = FORCE_ITEM_OVERHEAD_PAIRS;  // tuning: fixed cost of a work item, in pair units
-  int step_mode = -1;     // 1 GPU: -1 = automatic (2 when the particles fit one cluster, else 3 when they fit the chip, else 0), 0 = CUDA graph of 3 kernels per block step, 1 = persistent cooperative loop kernel, 2 = graph + cluster engine, 3 = graph + chip engine
+  int step_mode = -1;     // 1 GPU: -1 = automatic (2 when the particles fit one cluster, else 0), 0 = CUDA graph of 3 kernels per block step, 1 = persistent cooperative loop kernel, 2 = graph + cluster engine, 3 = graph + chip engine
   bool coop_ok = false;   // device supports cooperative launch
   int max_smem_optin = 0;  // largest dynamic shared memory a block may opt in to
   bool engine_ok = false;  // the cluster-engine kernel's attributes could be set
@@ -344,8 +344,10 @@ void decide_chip(al26_ctx *c) {
   GravDev &g = c->g;
   g.chip_max = 0;
   if (!c->chip_ok || !c->coop_ok || !c->committed || c->chip_max == 0 || g.n_loc != g.n_tot) return;
-  if (c->world == 1 ? (c->step_mode != 3 && c->step_mode != -1) : !is_p2p(c)) return;
-  if (c->world == 1 && c->engine_on) return;  // the cluster engine is the better tool where it fits
+  // one GPU: on request only (step mode 3) -- measured at N = 1e5 the ~12 us it needs per small block step (graph: 14 us)
+  // do not pay for a cooperative launch + state load in front of every bigger step, the runs being 3-8 steps long;
+  // peer-memory mode: automatic -- there a small step costs 21 us inside the loop kernel, on every rank
+  if (c->world == 1 ? c->step_mode != 3 : !is_p2p(c)) return;
   int p_cap = 0;
   const int nc = c->sm_count < CHIP_MAX_CTAS ? c->sm_count : CHIP_MAX_CTAS;
   if (!chip_plan(g.n_tot, nc, c->max_smem_optin, &p_cap) || !chip_fits(nc, p_cap, c->sm_count, c->max_smem_optin)) return;
@@ -359,7 +361,14 @@ void decide_chip(al26_ctx *c) {
   }
   g.chip_n = nc;
   g.chip_p = p_cap;
-  g.chip_max = c->chip_max > 0 ? (c->chip_max < CHIP_CAP ? c->chip_max : CHIP_CAP) : CHIP_MAX_ACT_DEFAULT;
+  // default: one GPU 32; peer-memory mode every block step that is not exchanged (below the split threshold)
+  int dflt = CHIP_MAX_ACT_DEFAULT;
+  if (c->world > 1) dflt = g.split_min - 1 < CHIP_CAP ? g.split_min - 1 : CHIP_CAP;
+  g.chip_max = c->chip_max > 0 ? (c->chip_max < CHIP_CAP ? c->chip_max : CHIP_CAP) : dflt;
+  if (g.chip_max < 1) {
+    g.chip_max = 0;
+    return;
+  }
   c->chip_on = true;
 }
 
@@ -511,7 +520,9 @@ int run_dist_chained(al26_ctx *c) {
       cudaError_t e = cudaSuccess;
       c->launches += launch_chip(c->g, -1, c->stream, &e);
       if (e != cudaSuccess) return fail(c, AL26_ECUDA, "chip-engine launch failed: %s", cudaGetErrorString(e));
-      c->launches += launch_loop_dist(c->g, MODE_STEP, -1, 1 << 30, 0ull, c->stream, &e);
+      // ONE step per launch: a big block is almost always followed by a run of small ones (it sits on a coarse level of
+      // the block-time hierarchy), and finding that out inside the loop kernel costs a whole scheduler pass
+      c->launches += launch_loop_dist(c->g, MODE_STEP, -1, 1, 0ull, c->stream, &e);
       if (e != cudaSuccess) return fail(c, AL26_ECUDA, "cooperative launch of the peer-memory loop kernel failed: %s", cudaGetErrorString(e));
       pairs_needed++;
     }

@@ -42,12 +42,19 @@ constexpr int CHIP_ENT = CHIP_MAX_CTAS / 32;  // header entries per lane of the 
 constexpr unsigned CHIP_SPIN_LIMIT = 1u << 22;
 
 struct alignas(32) ChipShared {
-  double red[CHIP_WARPS][7][32];
+  union {
+    double red[CHIP_WARPS][7][32];    // force phase: the warps' partial sums
+    double rowval[7][CHIP_MAX_CTAS];  // an owner, afterwards: the partial sums of one slot, by component and source CTA
+  };
+  double rsum[CHIP_WARPS][8];              // ... and their totals for a batch of slots
+  double4 c_pp[CHIP_MAX_CTAS], c_pv[CHIP_MAX_CTAS];  // every chunk's first record, fetched together with its header
+  int c_idx[CHIP_MAX_CTAS];
   double4 a_pp[CHIP_CAP], a_pv[CHIP_CAP];  // the step's active set (predicted), gathered from the owners' mail
   int a_idx[CHIP_CAP];
   unsigned long long cmin[CHIP_MAX_CTAS];  // every chunk's min(t + dt) ...
-  int ccount[CHIP_MAX_CTAS];               // ... and how many of its particles attain it
-  int own_cta[CHIP_MAX_CTAS], own_base[CHIP_MAX_CTAS], own_cnt[CHIP_MAX_CTAS];  // this step's owners, in CTA order
+  int ccount[CHIP_MAX_CTAS];               // ... how many of its particles attain it ...
+  unsigned cseq[CHIP_MAX_CTAS];            // ... and the step number its header and records carry
+  int own_cta[CHIP_MAX_CTAS], own_base[CHIP_MAX_CTAS];  // this step's owners, in CTA order, and their first slots
   unsigned long long wmin[CHIP_WARPS];
   unsigned long long tn_bits;
   int n_act, n_own, my_base, my_cnt, cand, pad[3];
@@ -57,7 +64,7 @@ static_assert(sizeof(ChipShared) % 32 == 0, "ChipShared must keep the double4 ar
 constexpr int CHIP_BYTES_PER_PARTICLE = 6 * 32 + 2 * 8;  // pos, vel, acc, jrk, ppos, pvel, t, dt
 
 int chip_smem_bytes(int p_cap) { return (int)sizeof(ChipShared) + p_cap * CHIP_BYTES_PER_PARTICLE; }
-size_t chip_mail_bytes(int n_ctas) { return (size_t)n_ctas * sizeof(ChipMail) + (size_t)n_ctas * sizeof(unsigned); }
+size_t chip_mail_bytes(int n_ctas) { return (size_t)n_ctas * sizeof(ChipMail) + (size_t)CHIP_CAP * n_ctas * 16 * sizeof(unsigned long long); }
 
 // n particles over n_ctas CTAs: per-CTA capacity, or false when the chunks do not fit `max_smem` bytes per block
 bool chip_plan(int n, int n_ctas, int max_smem, int *p_cap_out) {
@@ -70,6 +77,17 @@ bool chip_plan(int n, int n_ctas, int max_smem, int *p_cap_out) {
 
 namespace {
 
+// Everything that crosses CTAs travels as 64-bit words {step number (high half) | 32 bits of payload}, written and read
+// with volatile (L2) accesses: a reader polls the very words it needs until they carry the step number it expects, so a
+// message needs neither a flag, nor a fence, nor a second round trip, and no word is ever paired with a stale
+// neighbour.  Re-use of a buffer is ordered by data flow: a writer overwrites a word only after it has consumed values
+// that its readers computed from the previous contents.
+__device__ __forceinline__ void stv_2u64(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ldv_2u64(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ unsigned long long ldv_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -83,21 +101,28 @@ __device__ __forceinline__ unsigned ldv_u32(const unsigned *p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void stv_u32(unsigned *p, unsigned v) {
-  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+constexpr unsigned long long TAG_MASK = 0xffffffff00000000ull;
+__device__ __forceinline__ unsigned long long tag_of(unsigned seq) { return (unsigned long long)seq << 32; }
+// one double as two tagged words {hi, lo} in one 16-byte store
+__device__ __forceinline__ void put_double(unsigned long long *w, unsigned long long tag, double x) {
+  stv_2u64(w, tag | (unsigned)__double2hiint(x), tag | (unsigned)__double2loint(x));
 }
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ bool get_double(const unsigned long long *w, unsigned long long tag, double &x) {
+  unsigned long long a, b;
+  ldv_2u64(w, a, b);
+  x = __hiloint2double((int)(unsigned)a, (int)(unsigned)b);
+  return (a & TAG_MASK) == tag && (b & TAG_MASK) == tag;
+}
 
 // Block-wide poll: every thread evaluates `ready()` (threads with nothing to wait for return true) until all do.
 // Bounded: a protocol error raises hdr->loop_error (code 5) instead of hanging the GPU; returns false when the launch
-// must be abandoned (uniform over the block).  Ends with a gpu-scope acquire by the polling threads; the block barrier
-// inside __syncthreads_and hands the visibility on to the other threads, which read remote data with ld.cg only.
+// must be abandoned (uniform over the block).
 template <class F>
 __device__ __forceinline__ bool chip_poll(GravHeader *hdr, F ready) {
   unsigned spins = 0;
   while (true) {
     const bool ok = ready();
-    if (__syncthreads_and(ok)) break;
+    if (__syncthreads_and(ok)) return true;
     if ((++spins & 1023u) == 0u) {
       int bad = 0;
       if (threadIdx.x == 0) {
@@ -107,22 +132,20 @@ __device__ __forceinline__ bool chip_poll(GravHeader *hdr, F ready) {
       if (__syncthreads_or(bad)) return false;
     }
   }
-  fence_gpu();
-  return true;
 }
 
-// header of one chunk: three self-validating words (step number in the high half), so a reader can never pair a new
-// step number with an old value and the writer needs no fence between them
+// header of one chunk: {step | hi(min t+dt)}, {step | lo}, {step | count}
 __device__ __forceinline__ void mail_put_header(ChipMail *m, unsigned seq, unsigned long long min_bits, int count) {
-  const unsigned long long tag = (unsigned long long)seq << 32;
-  stv_u64(&m->w[0], tag | (min_bits >> 32));
-  stv_u64(&m->w[1], tag | (min_bits & 0xffffffffull));
+  const unsigned long long tag = tag_of(seq);
+  stv_2u64(&m->w[0], tag | (min_bits >> 32), tag | (min_bits & 0xffffffffull));
   stv_u64(&m->w[2], tag | (unsigned long long)(unsigned)count);
 }
 __device__ __forceinline__ bool mail_get_header(const ChipMail *m, unsigned seq, unsigned long long &min_bits, int &count) {
-  const unsigned long long tag = (unsigned long long)seq << 32, hi = 0xffffffff00000000ull;
-  const unsigned long long w0 = ldv_u64(&m->w[0]), w1 = ldv_u64(&m->w[1]), w2 = ldv_u64(&m->w[2]);
-  if ((w0 & hi) != tag || (w1 & hi) != tag || (w2 & hi) != tag) return false;
+  const unsigned long long tag = tag_of(seq);
+  unsigned long long w0, w1;
+  ldv_2u64(&m->w[0], w0, w1);
+  const unsigned long long w2 = ldv_u64(&m->w[2]);
+  if ((w0 & TAG_MASK) != tag || (w1 & TAG_MASK) != tag || (w2 & TAG_MASK) != tag) return false;
   min_bits = (w0 << 32) | (w1 & 0xffffffffull);
   count = (int)(unsigned)(w2 & 0xffffffffull);
   return true;
@@ -173,20 +196,36 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
   }
 
   ChipMail *mail = reinterpret_cast<ChipMail *>(g.chip_mail);
-  unsigned *flag = reinterpret_cast<unsigned *>(mail + nc);
+  unsigned long long *rows = reinterpret_cast<unsigned long long *>(mail + nc);  // [slot][CTA][16]
   ChipMail *mine = mail + me;
   unsigned seq = g.hdr->chip_seq + 1u;  // step numbers go on from launch to launch (the last one is left in the header)
 
   const int per = (g.n_tot + nc - 1) / nc;
   const int j0 = min(me * per, g.n_tot), cnt = min(per, g.n_tot - j0);
+  // peer-memory mode: the loop kernel's last block step was an exchanged one and nothing has passed over the state
+  // since -- the records the peers staged for it are pulled into the local state here, as that kernel's next scheduler
+  // pass would have done
+  const bool pull = g.p2p && g.hdr->dist_prev_exch != 0;
+  const unsigned pull_tag = (unsigned)g.hdr->dist_step;
+  StagingView sv;
+  if (pull) sv = staging_view(g.slab[g.rank], g.n_tot, (int)(g.hdr->dist_step & 1ull));
   for (int k = tid; k < cnt; k += CHIP_T) {
     const int i = j0 + k;
-    pos[k] = g.pos[i]; vel[k] = g.vel[i]; acc[k] = g.acc[i]; jrk[k] = g.jrk[i];
-    tt[k] = g.t[i]; dtt[k] = g.dt[i];
+    if (pull && sv.tag[i] == pull_tag) {
+      const double4 p = sv.pos[i], v = sv.vel[i], a = sv.acc[i], j = sv.jrk[i];
+      const double ti = sv.t[i], dti = sv.dt[i];
+      g.pos[i] = p; g.vel[i] = v; g.acc[i] = a; g.jrk[i] = j;
+      g.t[i] = ti; g.dt[i] = dti;
+      pos[k] = p; vel[k] = v; acc[k] = a; jrk[k] = j;
+      tt[k] = ti; dtt[k] = dti;
+    } else {
+      pos[k] = g.pos[i]; vel[k] = g.vel[i]; acc[k] = g.acc[i]; jrk[k] = g.jrk[i];
+      tt[k] = g.t[i]; dtt[k] = g.dt[i];
+    }
   }
   __syncthreads();
 
-  // this chunk's min(t + dt), the particles that attain it predicted to that time, then the header
+  // this chunk's min(t + dt), the particles that attain it predicted to that time (tagged records), then the header
   auto publish = [&](const unsigned s) {
     unsigned long long v = INF_BITS;
     for (int k = tid; k < cnt; k += CHIP_T) {
@@ -201,35 +240,56 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
 #pragma unroll
     for (int w = 1; w < CHIP_WARPS; w++) m = S.wmin[w] < m ? S.wmin[w] : m;
     const double tm = bitsd(m);
+    const unsigned long long tag = tag_of(s);
     for (int k = tid; k < cnt; k += CHIP_T) {
       if (dbits(tt[k] + dtt[k]) == m) {
         const int slot = atomicAdd(&S.cand, 1);  // the order of the slots is irrelevant to the results
         if (slot < CHIP_CAP) {
           double4 pp, pv;
           predict_to(tm, tt[k], pos[k], vel[k], acc[k], jrk[k], pp, pv);
-          mine->idx[slot] = j0 + k;
-          mine->pp[slot] = pp;
-          mine->pv[slot] = pv;
+          unsigned long long *r = mine->rec[slot];
+          put_double(r + 0, tag, pp.x); put_double(r + 2, tag, pp.y); put_double(r + 4, tag, pp.z); put_double(r + 6, tag, pp.w);
+          put_double(r + 8, tag, pv.x); put_double(r + 10, tag, pv.y); put_double(r + 12, tag, pv.z);
+          stv_2u64(r + 14, tag | (unsigned)(j0 + k), tag);
         }
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      fence_gpu();  // release: the records (made visible to this thread by the barrier) before the header
-      mail_put_header(mine, s, m, S.cand);
-    }
+    if (tid == 0) mail_put_header(mine, s, m, S.cand);
   };
 
   publish(seq);
   // the first step needs everybody's header
-  bool alive = chip_poll(g.hdr, [&]() {
-    if (tid >= nc) return true;
-    unsigned long long mb;
-    int c;
-    if (!mail_get_header(mail + tid, seq, mb, c)) return false;
-    S.cmin[tid] = mb;
-    S.ccount[tid] = c;
+  // one word of chunk c's first record into the cache; false while it does not carry step number s yet
+  auto fetch_rec0_word = [&](const int c, const int w, const unsigned s) {
+    const unsigned long long x = ldv_u64(&mail[c].rec[0][w]);
+    if ((x & TAG_MASK) != tag_of(s)) return false;
+    const unsigned half = (unsigned)x;
+    if (w < 8) reinterpret_cast<unsigned *>(&S.c_pp[c])[(w & ~1) | ((w & 1) ^ 1)] = half;  // words are {hi, lo}
+    else if (w < 14) reinterpret_cast<unsigned *>(&S.c_pv[c])[((w - 8) & ~1) | ((w & 1) ^ 1)] = half;
+    else if (w == 14) S.c_idx[c] = (int)half;
+    else S.c_pv[c].w = 0.0;
     return true;
+  };
+  bool alive = chip_poll(g.hdr, [&]() {
+    bool ok = true;
+    if (tid < nc) {
+      unsigned long long mb;
+      int c;
+      if (mail_get_header(mail + tid, seq, mb, c)) {
+        S.cmin[tid] = mb;
+        S.ccount[tid] = c;
+        S.cseq[tid] = seq;
+      } else {
+        ok = false;
+      }
+    }
+    for (int it = tid; it < nc * 16; it += CHIP_T) {
+      const int c = it >> 4;
+      // an empty chunk (no particles, or none below +inf) publishes no record
+      if (c * per < g.n_tot && !fetch_rec0_word(c, it & 15, seq)) ok = false;
+    }
+    return ok;
   });
 
   long long prof[6] = {0, 0, 0, 0, 0, 0}, tk = clock64();  // CTA 0 / thread 0: cycles per segment (al26_grav_loop_profile)
@@ -246,20 +306,27 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
   unsigned long long tnb = INF_BITS;
 
   while (alive) {
-    // ---- 1: block time, owners, slot numbering (warp 0, from the copies of the headers) -----------
-    __syncthreads();  // cmin / ccount complete (the polling threads wrote them)
+    // ---- 1: block time, owners, slot numbering (warp 0, from the copies of the headers; the poll that filled them
+    //         ended with a block barrier) ---------------------------------------------------------------------------
     if (warp == 0) {
+      unsigned long long cm[CHIP_ENT];  // this lane's entries, all loads in flight at once
+      int cc[CHIP_ENT];
       unsigned long long mymin = INF_BITS;
-      for (int q = 0; q < ent; q++) {
+#pragma unroll
+      for (int q = 0; q < CHIP_ENT; q++) {
         const int e = lane * ent + q;
-        if (e < nc) mymin = S.cmin[e] < mymin ? S.cmin[e] : mymin;
+        const bool in = q < ent && e < nc;
+        cm[q] = in ? S.cmin[e] : INF_BITS;
+        cc[q] = in ? S.ccount[e] : 0;
       }
+#pragma unroll
+      for (int q = 0; q < CHIP_ENT; q++) mymin = cm[q] < mymin ? cm[q] : mymin;
       const unsigned long long tn_b = warp_min_u64(mymin);
       int c_l = 0, o_l = 0;
-      for (int q = 0; q < ent; q++) {
-        const int e = lane * ent + q;
-        if (e < nc && S.cmin[e] == tn_b) {
-          c_l += S.ccount[e];
+#pragma unroll
+      for (int q = 0; q < CHIP_ENT; q++) {
+        if (cm[q] == tn_b && tn_b != INF_BITS) {
+          c_l += cc[q];
           o_l += 1;
         }
       }
@@ -278,17 +345,17 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         S.my_base = 0;
       }
       __syncwarp();
-      for (int q = 0; q < ent; q++) {
-        const int e = lane * ent + q;
-        if (e < nc && S.cmin[e] == tn_b) {
+#pragma unroll
+      for (int q = 0; q < CHIP_ENT; q++) {
+        if (cm[q] == tn_b && tn_b != INF_BITS) {
+          const int e = lane * ent + q;
           S.own_cta[opos] = e;
           S.own_base[opos] = base;
-          S.own_cnt[opos] = S.ccount[e];
           if (e == me) {
             S.my_base = base;
-            S.my_cnt = S.ccount[e];
+            S.my_cnt = cc[q];
           }
-          base += S.ccount[e];
+          base += cc[q];
           opos++;
         }
       }
@@ -303,25 +370,51 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     const int n_act = S.n_act, n_own = S.n_own;
     const double tn = bitsd(tnb);
     if (tn > span || n_act > max_act) break;  // uniform: a block for the whole chip, or the call is over
-    // ---- 2: the owners' records (one L2 round trip), meanwhile the predictor on the own chunk --------------------
-    if (tid < n_act) {
-      int k = 0;
-      while (k + 1 < n_own && S.own_base[k + 1] <= tid) k++;
-      const ChipMail *m = mail + S.own_cta[k];
-      const int r = tid - S.own_base[k];
-      S.a_idx[tid] = __ldcg(&m->idx[r]);
-      S.a_pp[tid] = ldcg_d4(&m->pp[r]);
-      S.a_pv[tid] = ldcg_d4(&m->pv[r]);
-    }
+    PROF(0)
+    // ---- 2: the predictor on the own chunk, then the owners' records: 16 threads per active particle poll its 16
+    //         tagged words (published before the owner's header, so normally there at the first look) ---------------
     for (int k = tid; k < cnt; k += CHIP_T) {
       double4 pp, pv;
       predict_to(tn, tt[k], pos[k], vel[k], acc[k], jrk[k], pp, pv);
       ppos[k] = pp;
       pvel[k] = pv;
     }
-    __syncthreads();
-    PROF(0)
-    // ---- 3: force of the active set against this chunk, one partial per slot ---------------------------------------
+    if (tid < n_own) {  // every owner's first record came with its header
+      const int c = S.own_cta[tid], slot = S.own_base[tid];
+      S.a_pp[slot] = S.c_pp[c];
+      S.a_pv[slot] = S.c_pv[c];
+      S.a_idx[slot] = S.c_idx[c];
+    }
+    if (n_act == n_own) __syncthreads();  // (nothing else to fetch: the barrier the poll below would have been)
+    for (int s0 = 0; s0 < n_act && alive && n_act > n_own; s0 += CHIP_T / 16) {
+      const int slot = s0 + (tid >> 4), w = tid & 15;
+      const unsigned long long *src = nullptr;
+      unsigned long long want = 0;
+      if (slot < n_act) {
+        int k = 0;
+        while (k + 1 < n_own && S.own_base[k + 1] <= slot) k++;
+        const int c = S.own_cta[k];
+        if (slot > S.own_base[k]) {
+          src = &mail[c].rec[slot - S.own_base[k]][w];
+          want = tag_of(S.cseq[c]);
+        }
+      }
+      alive = chip_poll(g.hdr, [&]() {
+        if (!src) return true;
+        const unsigned long long x = ldv_u64(src);
+        if ((x & TAG_MASK) != want) return false;
+        const unsigned half = (unsigned)x;
+        if (w < 8) reinterpret_cast<unsigned *>(&S.a_pp[slot])[(w & ~1) | ((w & 1) ^ 1)] = half;  // words are {hi, lo}
+        else if (w < 14) reinterpret_cast<unsigned *>(&S.a_pv[slot])[((w - 8) & ~1) | ((w & 1) ^ 1)] = half;
+        else if (w == 14) S.a_idx[slot] = (int)half;
+        else S.a_pv[slot].w = 0.0;
+        return true;
+      });
+    }
+    if (!alive) break;  // (the poll's barrier also covers the predictor's stores)
+    PROF(1)
+    // ---- 3: force of the active set against this chunk; one tagged row of partial sums per slot --------------------
+    const unsigned long long tag = tag_of(seq);
     for (int t0 = 0; t0 < n_act; t0 += 32) {
       const int nt = min(32, n_act - t0);
       int iw = 1;
@@ -340,57 +433,69 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         s.jy += __shfl_xor_sync(0xffffffffu, s.jy, o); s.jz += __shfl_xor_sync(0xffffffffu, s.jz, o);
         s.pot += __shfl_xor_sync(0xffffffffu, s.pot, o);
       }
+      if (t0 > 0) __syncthreads();  // red[] of the previous tile has been read
       if (lane < iw) {
         S.red[warp][0][lane] = s.ax; S.red[warp][1][lane] = s.ay; S.red[warp][2][lane] = s.az;
         S.red[warp][3][lane] = s.jx; S.red[warp][4][lane] = s.jy; S.red[warp][5][lane] = s.jz;
         S.red[warp][6][lane] = s.pot;
       }
       __syncthreads();
-      if (tid < 16 * nt) {  // 16 lanes per slot: fixed xor-butterfly over the warps' rows
-        const int sl = tid >> 4, row = tid & 15;
+      if (tid < 16 * nt) {  // 16 lanes per slot: fixed xor-butterfly over the warps' rows, then lane w stores word w
+        const int sl = tid >> 4, w = tid & 15;
         double r[7];
 #pragma unroll
-        for (int c = 0; c < 7; c++) r[c] = S.red[row][c][sl];
+        for (int c = 0; c < 7; c++) r[c] = S.red[w][c][sl];
         const unsigned mask = __activemask();
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
           for (int c = 0; c < 7; c++) r[c] += __shfl_xor_sync(mask, r[c], o);
         }
-        if (row == 0) {
-          const long long o = (long long)(t0 + sl) * nc + me;
-          g.part_a[o] = make_double4(r[0], r[1], r[2], r[6]);
-          g.part_j[o] = make_double4(r[3], r[4], r[5], 0.0);
-        }
+        double val = r[0];
+#pragma unroll
+        for (int c = 1; c < 7; c++) val = ((w >> 1) == c) ? r[c] : val;
+        const unsigned half = (w & 1) ? (unsigned)__double2loint(val) : (unsigned)__double2hiint(val);
+        if (w < 14) stv_u64(&rows[((size_t)(t0 + sl) * nc + me) * 16 + w], tag | half);
       }
-      __syncthreads();  // red[] is free for the next tile; all partial stores precede the flag
     }
-    if (tid == 0) {
-      fence_gpu();  // release: the partials before the flag
-      stv_u32(&flag[me], seq);
-    }
-    PROF(1)
-    // ---- 4: an owner sums its slots' partials, corrects them on the resident state and publishes its new header ----
+    PROF(2)
+    // ---- 4: an owner collects the rows of its slots (polling the words themselves), sums them in CTA order, corrects
+    //         the particles on the resident state and publishes its new header + records ----------------------------
     const int my_cnt = S.my_cnt, my_base = S.my_base;
     if (my_cnt > 0) {
-      alive = chip_poll(g.hdr, [&]() { return tid >= nc || ldv_u32(&flag[tid]) == seq; });
-      if (!alive) break;
-      for (int q = warp; q < my_cnt; q += CHIP_WARPS) {
-        const int slot = my_base + q;
-        double r[7] = {0, 0, 0, 0, 0, 0, 0};
-        const long long row = (long long)slot * nc;
-        for (int c = lane; c < nc; c += 32) {
-          const double4 pa = ldcg_d4(&g.part_a[row + c]), pj = ldcg_d4(&g.part_j[row + c]);
-          r[0] += pa.x; r[1] += pa.y; r[2] += pa.z; r[6] += pa.w;
-          r[3] += pj.x; r[4] += pj.y; r[5] += pj.z;
-        }
+      for (int q0 = 0; q0 < my_cnt && alive; q0 += CHIP_WARPS) {
+        const int nq = min(CHIP_WARPS, my_cnt - q0);
+        for (int q = 0; q < nq && alive; q++) {
+          if (q > 0) __syncthreads();  // the previous slot's sums have been taken out of rowval
+          const unsigned long long *row = rows + (size_t)(my_base + q0 + q) * nc * 16;
+          // item = (CTA c, component): thread t takes items t, t + 512, ...; every item is one 16-byte load
+          alive = chip_poll(g.hdr, [&]() {
+            bool ok = true;
+            for (int it = tid; it < nc * 7; it += CHIP_T) {
+              const int c = it / 7, comp = it - c * 7;
+              double x;
+              if (get_double(row + (size_t)c * 16 + 2 * comp, tag, x)) S.rowval[comp][c] = x;
+              else ok = false;
+            }
+            return ok;
+          });
+          if (!alive) break;
+          if (warp < 7) {  // component `warp`: lanes sum every 32nd CTA in order, then a fixed butterfly
+            double a = 0.0;
+            for (int c = lane; c < nc; c += 32) a += S.rowval[warp][c];
 #pragma unroll
-        for (int c = 0; c < 7; c++) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) S.rsum[q][warp] = a;
+          }
         }
-        if (lane == 0) {
+        if (!alive) break;
+        __syncthreads();
+        if (lane == 0 && warp < nq) {  // one corrector per warp
+          const int slot = my_base + q0 + warp;
           const int i = S.a_idx[slot], k = i - j0;
+          double r[7];
+#pragma unroll
+          for (int c = 0; c < 7; c++) r[c] = S.rsum[warp][c];
           SlotIn in;
           in.i = i;
           in.a0 = acc[k]; in.j0 = jrk[k];
@@ -402,23 +507,34 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
           pos[k] = ns.pos; vel[k] = ns.vel; acc[k] = ns.acc; jrk[k] = ns.jrk;
           tt[k] = ns.t; dtt[k] = ns.dt;
         }
+        __syncthreads();
       }
-      __syncthreads();
+      if (!alive) break;
       publish(seq + 1u);
     }
-    PROF(2)
+    PROF(3)
     // ---- 5: everybody waits for the owners' headers (the other chunks' minima cannot have changed) ---------------
     alive = chip_poll(g.hdr, [&]() {
-      if (tid >= n_own) return true;
-      const int c = S.own_cta[tid];
-      unsigned long long mb;
-      int cc;
-      if (!mail_get_header(mail + c, seq + 1u, mb, cc)) return false;
-      S.cmin[c] = mb;
-      S.ccount[c] = cc;
-      return true;
+      bool ok = true;
+      for (int k = warp; k < n_own; k += CHIP_WARPS) {  // lane 0: the header; lanes 16-31: the first record
+        const int c = S.own_cta[k];
+        if (lane == 0) {
+          unsigned long long mb;
+          int cc;
+          if (mail_get_header(mail + c, seq + 1u, mb, cc)) {
+            S.cmin[c] = mb;
+            S.ccount[c] = cc;
+            S.cseq[c] = seq + 1u;
+          } else {
+            ok = false;
+          }
+        } else if (lane >= 16) {
+          if (!fetch_rec0_word(c, lane - 16, seq + 1u)) ok = false;
+        }
+      }
+      return ok;
     });
-    PROF(3)
+    PROF(4)
     seq += 1u;
     n_steps += 1;
     if (me == 0 && tid == 0) {
@@ -438,6 +554,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     if (alive) ctl->t_next_bits = tnb;  // the block time of the step that is still to be taken (or beyond the span)
     g.hdr->chip_seq = seq;
     g.hdr->bar_counter = 0u;  // chained: the loop kernel that follows counts its grid barriers from zero
+    if (pull) g.hdr->dist_prev_exch = 0;  // every CTA has read the flag: none leaves before all have published
     g.hdr->n_steps += n_steps;
     g.hdr->n_pairs += n_pairs;
     g.hdr->n_chip += n_steps;

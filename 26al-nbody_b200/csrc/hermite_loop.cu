@@ -460,7 +460,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   // a function of the global active count, hence the same on every rank; ranks drift apart during such steps
   // and meet again at the next exchange.
   unsigned long long xid = xid0;
-  bool prev_exch = (MODE == MODE_STEP) && g.hdr->dist_prev_exch != 0;
+  // the last block step of the call may itself have been an exchanged one (a dyadic span ends on a coarse level of the
+  // block-time hierarchy): the synchronisation step pulls what it staged, like any block step would
+  bool prev_exch = (MODE != MODE_INIT) && g.hdr->dist_prev_exch != 0;
   // the next block time: written by k_begin (identical on every rank) or by the previous launch
   unsigned long long tnext_bits = __ldcg(&g.ctrl[phase0].t_next_bits);
   for (int step = 0; step < max_steps; step++) {

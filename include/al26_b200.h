@@ -213,7 +213,7 @@ int al26_set_big_block(al26_ctx *ctx, int n_act_min);
  * applies at the next al26_grav_commit */
 int al26_set_decomposition(al26_ctx *ctx, int max_rounds, double item_overhead_pairs);
 /* tuning hook: how block steps are driven on one GPU.  -1 (default): automatic -- 2 when the particles fit one
- * cluster (N <= ~13000), else 3 when they fit the chip (N <= ~1.2e5), else 0.  0: a CUDA graph of three kernels per block
+ * cluster (N <= ~13000), else 0.  0: a CUDA graph of three kernels per block
  * step, relaunched until the device reports the call done; 1: one persistent cooperative kernel runs the
  * whole predict -> force -> correct loop with grid barriers (the form the multi-GPU peer-memory mode uses).
  * Bit-identical results (except the loop kernel's fused small steps, al26_set_fuse_max: identical integer work,
@@ -235,7 +235,8 @@ int al26_grav_engine_steps(al26_ctx *ctx, int64_t *n_engine, int *cluster_size);
  * particles per CTA, shared memory per CTA */
 int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *particles_per_cta, int *smem_bytes);
 /* step mode 3 = the graph with the CHIP ENGINE in front of every block step, for the particle sets that do not fit one
- * cluster (automatic from N ~ 1.3e4 up to ~1.2e5 on B200: 144 + 64 B per particle in the shared memory of 148 SMs):
+ * cluster (up to N ~ 1.1e5 on B200: 144 + 64 B per particle in the shared memory of 148 SMs; on request only on one GPU,
+ * automatic in the peer-memory multi-GPU mode):
  * one CTA per SM keeps a contiguous chunk of the particles resident for a whole run of small block steps; the CTAs
  * talk through single-writer records in L2 that carry their step number (no grid barrier, no atomics): the chunk's
  * min(t + dt) with the particles that attain it already predicted, one force partial per (active particle, chunk),
