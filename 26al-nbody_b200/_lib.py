@@ -103,6 +103,7 @@ SIGNATURES = {
     "al26_dbg_engine_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "al26_set_chip_max": (C.c_int, [_VP, C.c_int]),
     "al26_grav_chip_steps": (C.c_int, [_VP, _PI64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "al26_dbg_chip_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _PI64]),
     "al26_set_fuse_max": (C.c_int, [_VP, C.c_int]),
     "al26_grav_fused_steps": (C.c_int, [_VP, _PI64]),
     "al26_grav_fuse_profile": (C.c_int, [_VP, _PI64]),
@@ -263,6 +264,11 @@ class Context:
         names = ("force_arrive", "wait_partials", "reduce_correct", "-", "wait_release", "fused_total", "scan", "barrier")
         return {k: v for k, v in zip(names, list(h)) if k != "-"}
 
+    def fuse_profile_raw(self):
+        h = (C.c_int64 * 16)()
+        self.chk(self.L.al26_grav_fuse_profile(self.h, h))
+        return list(h)
+
     def dist_profile(self):
         """peer-memory mode: CTA 0's SM cycles per step category since the last commit (include/al26_b200.h)"""
         h = (C.c_int64 * 12)()
@@ -397,6 +403,15 @@ def decomposition(n_act, n_tot, sm_count=148, variant=0, big_nact=2048):
     if rc != 0:
         raise Al26Error(rc, "bad arguments")
     return dict(zip(("ipt", "ti", "n_itiles", "n_jsplit", "jchunk", "slot_stride", "part_capacity", "grid"), list(out)))
+
+
+def chip_plan(n, n_ctas=148, max_smem_per_block=232448):
+    """host-only: (particles per CTA or 0, shared-memory bytes per CTA, HBM bytes of mail + partial rows) of the chip engine"""
+    p, b, m = C.c_int(0), C.c_int(0), C.c_int64(0)
+    rc = load().al26_dbg_chip_plan(int(n), int(n_ctas), int(max_smem_per_block), C.byref(p), C.byref(b), C.byref(m))
+    if rc:
+        raise Al26Error(rc, "al26_dbg_chip_plan: invalid argument")
+    return p.value, b.value, m.value
 
 
 def engine_plan(n, max_smem_per_block=232448):

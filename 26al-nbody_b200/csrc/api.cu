@@ -1429,6 +1429,20 @@ int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *
   return 0;
 }
 
+int al26_dbg_chip_plan(int n, int n_ctas, int max_smem_per_block, int *particles_per_cta, int *smem_bytes, int64_t *mail_bytes) {
+  if (!particles_per_cta || !smem_bytes || !mail_bytes || n < 1 || n_ctas < 1 || max_smem_per_block < 0) return AL26_EINVAL;
+  int p_cap = 0;
+  if (!chip_plan(n, n_ctas, max_smem_per_block, &p_cap)) {
+    *particles_per_cta = *smem_bytes = 0;
+    *mail_bytes = 0;
+    return 0;
+  }
+  *particles_per_cta = p_cap;
+  *smem_bytes = chip_smem_bytes(p_cap);
+  *mail_bytes = (int64_t)chip_mail_bytes(n_ctas);
+  return 0;
+}
+
 int al26_set_force_variant(al26_ctx *c, int variant) {
   if (!c) return AL26_EINVAL;
   if (variant < 0 || variant >= force_variant_count()) return fail(c, AL26_EINVAL, "force variant %d out of range", variant);

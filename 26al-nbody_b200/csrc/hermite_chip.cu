@@ -49,6 +49,7 @@ struct alignas(32) ChipShared {
   double rsum[CHIP_WARPS][8];              // ... and their totals for a batch of slots
   double4 c_pp[CHIP_MAX_CTAS], c_pv[CHIP_MAX_CTAS];  // every chunk's first record, fetched together with its header
   int c_idx[CHIP_MAX_CTAS];
+  unsigned c_seq[CHIP_MAX_CTAS];  // the step number of the cached first record (valid when equal to cseq)
   double4 a_pp[CHIP_CAP], a_pv[CHIP_CAP];  // the step's active set (predicted), gathered from the owners' mail
   int a_idx[CHIP_CAP];
   unsigned long long cmin[CHIP_MAX_CTAS];  // every chunk's min(t + dt) ...
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
   double *tt = reinterpret_cast<double *>(pvel + p_cap), *dtt = tt + p_cap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int me = blockIdx.x, nc = gridDim.x;
+  const long long t_entry = clock64();
 
   const int phase = phase_arg < 0 ? g.hdr->phase : phase_arg;
   StepCtrl *ctl = &g.ctrl[phase];
@@ -268,31 +270,26 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     if (w < 8) reinterpret_cast<unsigned *>(&S.c_pp[c])[(w & ~1) | ((w & 1) ^ 1)] = half;  // words are {hi, lo}
     else if (w < 14) reinterpret_cast<unsigned *>(&S.c_pv[c])[((w - 8) & ~1) | ((w & 1) ^ 1)] = half;
     else if (w == 14) S.c_idx[c] = (int)half;
-    else S.c_pv[c].w = 0.0;
+    else {
+      S.c_pv[c].w = 0.0;
+      S.c_seq[c] = s;  // (the poll this runs in only ends when all 16 words were there in the same round)
+    }
     return true;
   };
   bool alive = chip_poll(g.hdr, [&]() {
-    bool ok = true;
-    if (tid < nc) {
-      unsigned long long mb;
-      int c;
-      if (mail_get_header(mail + tid, seq, mb, c)) {
-        S.cmin[tid] = mb;
-        S.ccount[tid] = c;
-        S.cseq[tid] = seq;
-      } else {
-        ok = false;
-      }
-    }
-    for (int it = tid; it < nc * 16; it += CHIP_T) {
-      const int c = it >> 4;
-      // an empty chunk (no particles, or none below +inf) publishes no record
-      if (c * per < g.n_tot && !fetch_rec0_word(c, it & 15, seq)) ok = false;
-    }
-    return ok;
+    if (tid >= nc) return true;
+    unsigned long long mb;
+    int c;
+    if (!mail_get_header(mail + tid, seq, mb, c)) return false;
+    S.cmin[tid] = mb;
+    S.ccount[tid] = c;
+    S.cseq[tid] = seq;
+    S.c_seq[tid] = 0u;  // no record cached yet (step numbers start at 1)
+    return true;
   });
 
   long long prof[6] = {0, 0, 0, 0, 0, 0}, tk = clock64();  // CTA 0 / thread 0: cycles per segment (al26_grav_loop_profile)
+  prof[5] = tk - t_entry;                                  // [5]: the launch's prologue (state load, first publication, gather)
 #define PROF(k)                      \
   if (me == 0 && tid == 0) {         \
     const long long now = clock64(); \
@@ -321,7 +318,10 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       }
 #pragma unroll
       for (int q = 0; q < CHIP_ENT; q++) mymin = cm[q] < mymin ? cm[q] : mymin;
-      const unsigned long long tn_b = warp_min_u64(mymin);
+      // warp minimum of a 64-bit key with two 32-bit hardware reductions
+      const unsigned hi_min = __reduce_min_sync(0xffffffffu, (unsigned)(mymin >> 32));
+      const unsigned lo_min = __reduce_min_sync(0xffffffffu, (unsigned)(mymin >> 32) == hi_min ? (unsigned)mymin : 0xffffffffu);
+      const unsigned long long tn_b = ((unsigned long long)hi_min << 32) | lo_min;
       int c_l = 0, o_l = 0;
 #pragma unroll
       for (int q = 0; q < CHIP_ENT; q++) {
@@ -330,15 +330,14 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
           o_l += 1;
         }
       }
-      int c_inc = c_l, o_inc = o_l;  // inclusive scans over the lanes
+      // inclusive scans over the lanes, both in one word (owners < 2^9, active particles < 2^22)
+      int packed = c_l * 512 + o_l;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, c_inc, o), b = __shfl_up_sync(0xffffffffu, o_inc, o);
-        if (lane >= o) {
-          c_inc += a;
-          o_inc += b;
-        }
+        const int a = __shfl_up_sync(0xffffffffu, packed, o);
+        if (lane >= o) packed += a;
       }
+      const int c_inc = packed >> 9, o_inc = packed & 511;
       int base = c_inc - c_l, opos = o_inc - o_l;
       if (lane == 0) {
         S.my_cnt = 0;
@@ -379,14 +378,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       ppos[k] = pp;
       pvel[k] = pv;
     }
-    if (tid < n_own) {  // every owner's first record came with its header
-      const int c = S.own_cta[tid], slot = S.own_base[tid];
-      S.a_pp[slot] = S.c_pp[c];
-      S.a_pv[slot] = S.c_pv[c];
-      S.a_idx[slot] = S.c_idx[c];
-    }
-    if (n_act == n_own) __syncthreads();  // (nothing else to fetch: the barrier the poll below would have been)
-    for (int s0 = 0; s0 < n_act && alive && n_act > n_own; s0 += CHIP_T / 16) {
+    for (int s0 = 0; s0 < n_act && alive; s0 += CHIP_T / 16) {
       const int slot = s0 + (tid >> 4), w = tid & 15;
       const unsigned long long *src = nullptr;
       unsigned long long want = 0;
@@ -394,11 +386,18 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         int k = 0;
         while (k + 1 < n_own && S.own_base[k + 1] <= slot) k++;
         const int c = S.own_cta[k];
-        if (slot > S.own_base[k]) {
+        if (slot == S.own_base[k] && S.c_seq[c] == S.cseq[c]) {  // the chunk's first record came with its header
+          if (w == 0) {
+            S.a_pp[slot] = S.c_pp[c];
+            S.a_pv[slot] = S.c_pv[c];
+            S.a_idx[slot] = S.c_idx[c];
+          }
+        } else {
           src = &mail[c].rec[slot - S.own_base[k]][w];
           want = tag_of(S.cseq[c]);
         }
       }
+      if (!__syncthreads_or(src != nullptr)) continue;  // nothing to fetch (the barrier also covers the predictor's stores)
       alive = chip_poll(g.hdr, [&]() {
         if (!src) return true;
         const unsigned long long x = ldv_u64(src);
@@ -463,6 +462,8 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     //         the particles on the resident state and publishes its new header + records ----------------------------
     const int my_cnt = S.my_cnt, my_base = S.my_base;
     if (my_cnt > 0) {
+      long long o_t0 = 0, o_t1 = 0, o_t2 = 0;  // the owner's own clock: rows complete, corrected, published
+      if (tid == 0) o_t0 = clock64();
       for (int q0 = 0; q0 < my_cnt && alive; q0 += CHIP_WARPS) {
         const int nq = min(CHIP_WARPS, my_cnt - q0);
         for (int q = 0; q < nq && alive; q++) {
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
             return ok;
           });
           if (!alive) break;
+          if (tid == 0 && q0 == 0 && q == 0) o_t1 = clock64();
           if (warp < 7) {  // component `warp`: lanes sum every 32nd CTA in order, then a fixed butterfly
             double a = 0.0;
             for (int c = lane; c < nc; c += 32) a += S.rowval[warp][c];
@@ -510,7 +512,15 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         __syncthreads();
       }
       if (!alive) break;
+      if (tid == 0) o_t2 = clock64();
       publish(seq + 1u);
+      if (tid == 0) {  // diagnostic (al26_grav_fuse_profile): owner-side cycles per segment, over all owners
+        const long long o_t3 = clock64();
+        atomicAdd((unsigned long long *)&g.hdr->fuse_ns[0], (unsigned long long)(o_t1 - o_t0));
+        atomicAdd((unsigned long long *)&g.hdr->fuse_ns[1], (unsigned long long)(o_t2 - o_t1));
+        atomicAdd((unsigned long long *)&g.hdr->fuse_ns[2], (unsigned long long)(o_t3 - o_t2));
+        atomicAdd((unsigned long long *)&g.hdr->fuse_ns[3], 1ull);
+      }
     }
     PROF(3)
     // ---- 5: everybody waits for the owners' headers (the other chunks' minima cannot have changed) ---------------
@@ -558,6 +568,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     g.hdr->n_steps += n_steps;
     g.hdr->n_pairs += n_pairs;
     g.hdr->n_chip += n_steps;
+    g.hdr->fuse_ns[4] += 1;  // diagnostic: launches that got past the span check
     for (int k = 0; k < 6; k++) g.hdr->loop_cycles[k] += prof[k];
     for (int b = 0; b < 9; b++) g.hdr->nact_hist[b] += hist[b];
   }
@@ -590,7 +601,7 @@ int launch_chip(const GravDev &g, int phase, cudaStream_t s, cudaError_t *err) {
   cfg.dynamicSmemBytes = (size_t)chip_smem_bytes(g.chip_p);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // co-residency of all CTAs: they wait for each other's flags
+  attr[0].id = cudaLaunchAttributeCooperative;  // co-residency of all CTAs: they wait for each other's words
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;

@@ -14,6 +14,7 @@
 // also invalidates the SM's L1 so data written by other SMs in the previous phase is re-read from L2.
 // Co-residency of all CTAs is guaranteed by the cooperative launch.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "hermite_force.cuh"
 #include "hermite_step.cuh"

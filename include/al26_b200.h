@@ -249,6 +249,10 @@ int al26_dbg_engine_plan(int n, int max_smem_per_block, int *cluster_size, int *
  * gravity.evolve_model (al26_nbody.py:833). */
 int al26_set_chip_max(al26_ctx *ctx, int n_act_max);
 int al26_grav_chip_steps(al26_ctx *ctx, int64_t *n_chip, int *n_ctas, int *n_act_max);
+/* host-only diagnostic (needs no GPU): the chip engine's layout for n particles on n_ctas CTAs (one per SM) when a block
+ * may opt in to max_smem_per_block bytes -- particles per CTA (0 = the chunks do not fit), shared memory per CTA, and the
+ * bytes of the mail + partial-row buffers in HBM */
+int al26_dbg_chip_plan(int n, int n_ctas, int max_smem_per_block, int *particles_per_cta, int *smem_bytes, int64_t *mail_bytes);
 /* tuning hook of the persistent loop kernels (step mode 1 and the peer-memory multi-GPU mode), before commit:
  * block steps of at most n_act_max active particles (0..32; 0 = off; -1 = default: 32 when N <= 32768,
  * else off) take the fused small-step path

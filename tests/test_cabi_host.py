@@ -218,3 +218,22 @@ def test_cluster_engine_plan(pkg):
     assert lib.engine_plan(10_000, 100_000)[0] == 0      # a device with less shared memory: no engine
     with pytest.raises(lib.Al26Error):
         lib.engine_plan(0)
+
+
+def test_chip_engine_plan(pkg):
+    """host-side check of the chip engine's capacity plan (hermite_chip.cu: chip_plan): contiguous chunks of ceil(n / CTAs)
+    particles, 208 B each behind the fixed part, within the shared memory a block may opt in to"""
+    from importlib import import_module
+    lib = import_module("26al-nbody_b200._lib")
+    p, b, m = lib.chip_plan(100_000)                      # BASELINE config 3 on the 148 SMs of a B200
+    assert p == 680 and 148 * p >= 100_000 and b <= 232448
+    fixed = b - 208 * p
+    assert 0 < fixed < 80 * 1024 and m > 0
+    for n in (1, 2, 147, 148, 149, 4096, 20_000, 110_000):
+        p, b, _ = lib.chip_plan(n)
+        assert p % 8 == 0 and 148 * p >= n and (p - 8) * 148 < n + 8 * 148 and b == fixed + 208 * p
+    assert lib.chip_plan(1_000_000)[0] == 0                # config 4 does not fit the chip: the grid-wide kernels take it
+    assert lib.chip_plan(100_000, 148, 150_000)[0] == 0   # a device with less shared memory per block
+    assert lib.chip_plan(100_000, 300)[0] == 0            # more CTAs than the scheduling warp handles
+    with pytest.raises(pkg.Al26Error):
+        lib.chip_plan(0)

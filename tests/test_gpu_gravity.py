@@ -412,7 +412,10 @@ def test_error_codes_and_edge_cases(pkg, ctx):
         g.set_params(dt_min=1e-200)
     assert ei.value.code == -1
     with pytest.raises(pkg.Al26Error) as ei:
-        ctx.set_step_mode(3)
+        ctx.set_step_mode(4)
+    assert ei.value.code == -1
+    with pytest.raises(pkg.Al26Error) as ei:
+        ctx.set_chip_max(257)
     assert ei.value.code == -1
     # a single particle moves on a straight line
     g.commit(np.ones(1), np.zeros(1), np.zeros(1), np.zeros(1), np.array([1.0]), np.zeros(1), np.zeros(1))
