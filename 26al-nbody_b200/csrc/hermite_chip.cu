@@ -40,6 +40,7 @@ constexpr int CHIP_WARPS = CHIP_T / 32;
 static_assert(CHIP_WARPS == 16, "the cross-warp sum below is a 16-lane butterfly");
 constexpr int CHIP_ENT = CHIP_MAX_CTAS / 32;  // header entries per lane of the scheduling warp
 constexpr unsigned CHIP_SPIN_LIMIT = 1u << 22;
+constexpr int CHIP_FUSE_PREDICT = 4;  // blocks of at most this many particles predict j inside the pair loop
 
 struct alignas(32) ChipShared {
   union {
@@ -50,6 +51,9 @@ struct alignas(32) ChipShared {
   double4 c_pp[CHIP_MAX_CTAS], c_pv[CHIP_MAX_CTAS];  // every chunk's first record, fetched together with its header
   int c_idx[CHIP_MAX_CTAS];
   unsigned c_seq[CHIP_MAX_CTAS];  // the step number of the cached first record (valid when equal to cseq)
+  unsigned c_dte[CHIP_MAX_CTAS];  // ... and the exponent bits of that particle's timestep (a power of two)
+  unsigned a_dte[CHIP_CAP];       // the same for the step's active set
+  unsigned long long pred_bits;   // the block time ppos / pvel were predicted to ahead of time (0 = not valid)
   double4 a_pp[CHIP_CAP], a_pv[CHIP_CAP];  // the step's active set (predicted), gathered from the owners' mail
   int a_idx[CHIP_CAP];
   unsigned long long cmin[CHIP_MAX_CTAS];  // every chunk's min(t + dt) ...
@@ -58,7 +62,8 @@ struct alignas(32) ChipShared {
   int own_cta[CHIP_MAX_CTAS], own_base[CHIP_MAX_CTAS];  // this step's owners, in CTA order, and their first slots
   unsigned long long wmin[CHIP_WARPS];
   unsigned long long tn_bits;
-  int n_act, n_own, my_base, my_cnt, cand, pad[3];
+  int n_act, n_own, my_base, my_cnt, cand, acct_own, pad[2];
+  int hist[12];  // CTA 0: block steps by floor(log2(n_act))
 };
 static_assert(sizeof(ChipShared) % 32 == 0, "ChipShared must keep the double4 arrays behind it aligned");
 
@@ -152,6 +157,13 @@ __device__ __forceinline__ bool mail_get_header(const ChipMail *m, unsigned seq,
   return true;
 }
 
+// warp minimum of a 64-bit key with two 32-bit hardware reductions
+__device__ __forceinline__ unsigned long long warp_min_u64_redux(unsigned long long v) {
+  const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32));
+  const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32) == hi ? (unsigned)v : 0xffffffffu);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
 __device__ __forceinline__ void predict_to(const double tn, const double ti, const double4 p, const double4 v, const double4 a,
                                            const double4 j, double4 &pp, double4 &pv) {
   const double s = tn - ti;
@@ -234,13 +246,11 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       const unsigned long long cb = dbits(tt[k] + dtt[k]);
       v = cb < v ? cb : v;
     }
-    v = warp_min_u64(v);
+    v = warp_min_u64_redux(v);
     if (lane == 0) S.wmin[warp] = v;
     if (tid == 0) S.cand = 0;
     __syncthreads();
-    unsigned long long m = S.wmin[0];
-#pragma unroll
-    for (int w = 1; w < CHIP_WARPS; w++) m = S.wmin[w] < m ? S.wmin[w] : m;
+    const unsigned long long m = warp_min_u64_redux(S.wmin[lane & (CHIP_WARPS - 1)]);
     const double tm = bitsd(m);
     const unsigned long long tag = tag_of(s);
     for (int k = tid; k < cnt; k += CHIP_T) {
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
           unsigned long long *r = mine->rec[slot];
           put_double(r + 0, tag, pp.x); put_double(r + 2, tag, pp.y); put_double(r + 4, tag, pp.z); put_double(r + 6, tag, pp.w);
           put_double(r + 8, tag, pv.x); put_double(r + 10, tag, pv.y); put_double(r + 12, tag, pv.z);
-          stv_2u64(r + 14, tag | (unsigned)(j0 + k), tag);
+          stv_2u64(r + 14, tag | (unsigned)(j0 + k), tag | (unsigned)(dbits(dtt[k]) >> 52));
         }
       }
     }
@@ -272,6 +282,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     else if (w == 14) S.c_idx[c] = (int)half;
     else {
       S.c_pv[c].w = 0.0;
+      S.c_dte[c] = half;
       S.c_seq[c] = s;  // (the poll this runs in only ends when all 16 words were there in the same round)
     }
     return true;
@@ -296,8 +307,15 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     prof[k] += now - tk;             \
     tk = now;                        \
   }
+  // accounting (CTA 0 only) stays off the step's critical path: it lives in warp 2, which has nothing else to do
+  // between the phases, not in the warp that schedules
+  constexpr int ACCT_TID = 64;
   long long n_steps = 0, n_pairs = 0;
-  int hist[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (tid < 12) S.hist[tid] = 0;
+  if (tid == 0) {
+    S.acct_own = 0;
+    S.pred_bits = 0ull;
+  }
   const double eps2 = g.eps2;
   const int ent = (nc + 31) / 32;
   unsigned long long tnb = INF_BITS;
@@ -318,10 +336,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       }
 #pragma unroll
       for (int q = 0; q < CHIP_ENT; q++) mymin = cm[q] < mymin ? cm[q] : mymin;
-      // warp minimum of a 64-bit key with two 32-bit hardware reductions
-      const unsigned hi_min = __reduce_min_sync(0xffffffffu, (unsigned)(mymin >> 32));
-      const unsigned lo_min = __reduce_min_sync(0xffffffffu, (unsigned)(mymin >> 32) == hi_min ? (unsigned)mymin : 0xffffffffu);
-      const unsigned long long tn_b = ((unsigned long long)hi_min << 32) | lo_min;
+      const unsigned long long tn_b = warp_min_u64_redux(mymin);
       int c_l = 0, o_l = 0;
 #pragma unroll
       for (int q = 0; q < CHIP_ENT; q++) {
@@ -372,11 +387,18 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     PROF(0)
     // ---- 2: the predictor on the own chunk, then the owners' records: 16 threads per active particle poll its 16
     //         tagged words (published before the owner's header, so normally there at the first look) ---------------
-    for (int k = tid; k < cnt; k += CHIP_T) {
-      double4 pp, pv;
-      predict_to(tn, tt[k], pos[k], vel[k], acc[k], jrk[k], pp, pv);
-      ppos[k] = pp;
-      pvel[k] = pv;
+    // tiny blocks (<= CHIP_FUSE_PREDICT active particles, more than half of all block steps): every j is visited by at most
+    // that many lanes, so it is predicted on the fly in the pair loop -- the same arithmetic on the same operands, hence
+    // the same bits (the self pair still cancels exactly) -- instead of in a pass of its own through shared memory
+    const bool predicted = (S.pred_bits == tnb);  // (written two barriers ago)
+    const bool fused_predict = !predicted && n_act <= CHIP_FUSE_PREDICT;
+    if (!predicted && !fused_predict) {
+      for (int k = tid; k < cnt; k += CHIP_T) {
+        double4 pp, pv;
+        predict_to(tn, tt[k], pos[k], vel[k], acc[k], jrk[k], pp, pv);
+        ppos[k] = pp;
+        pvel[k] = pv;
+      }
     }
     for (int s0 = 0; s0 < n_act && alive; s0 += CHIP_T / 16) {
       const int slot = s0 + (tid >> 4), w = tid & 15;
@@ -391,6 +413,7 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
             S.a_pp[slot] = S.c_pp[c];
             S.a_pv[slot] = S.c_pv[c];
             S.a_idx[slot] = S.c_idx[c];
+            S.a_dte[slot] = S.c_dte[c];
           }
         } else {
           src = &mail[c].rec[slot - S.own_base[k]][w];
@@ -406,7 +429,10 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         if (w < 8) reinterpret_cast<unsigned *>(&S.a_pp[slot])[(w & ~1) | ((w & 1) ^ 1)] = half;  // words are {hi, lo}
         else if (w < 14) reinterpret_cast<unsigned *>(&S.a_pv[slot])[((w - 8) & ~1) | ((w & 1) ^ 1)] = half;
         else if (w == 14) S.a_idx[slot] = (int)half;
-        else S.a_pv[slot].w = 0.0;
+        else {
+          S.a_pv[slot].w = 0.0;
+          S.a_dte[slot] = half;
+        }
         return true;
       });
     }
@@ -423,9 +449,18 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       const double4 p = S.a_pp[li], v = S.a_pv[li];
       Acc7 s;
       s.ax = s.ay = s.az = s.jx = s.jy = s.jz = s.pot = 0.0;
+      if (fused_predict) {
+#pragma unroll 2
+        for (int jj = warp * jgroups + jsub; jj < cnt; jj += CHIP_WARPS * jgroups) {
+          double4 pp, pv;
+          predict_to(tn, tt[jj], pos[jj], vel[jj], acc[jj], jrk[jj], pp, pv);
+          pair_interaction(pp, pv, eps2, p.x, p.y, p.z, v.x, v.y, v.z, s);
+        }
+      } else {
 #pragma unroll 4
-      for (int jj = warp * jgroups + jsub; jj < cnt; jj += CHIP_WARPS * jgroups)
-        pair_interaction(ppos[jj], pvel[jj], eps2, p.x, p.y, p.z, v.x, v.y, v.z, s);
+        for (int jj = warp * jgroups + jsub; jj < cnt; jj += CHIP_WARPS * jgroups)
+          pair_interaction(ppos[jj], pvel[jj], eps2, p.x, p.y, p.z, v.x, v.y, v.z, s);
+      }
       for (int o = iw; o < 32; o <<= 1) {  // fixed butterfly over the lane bits above log2(iw)
         s.ax += __shfl_xor_sync(0xffffffffu, s.ax, o); s.ay += __shfl_xor_sync(0xffffffffu, s.ay, o);
         s.az += __shfl_xor_sync(0xffffffffu, s.az, o); s.jx += __shfl_xor_sync(0xffffffffu, s.jx, o);
@@ -456,6 +491,11 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
         const unsigned half = (w & 1) ? (unsigned)__double2loint(val) : (unsigned)__double2hiint(val);
         if (w < 14) stv_u64(&rows[((size_t)(t0 + sl) * nc + me) * 16 + w], tag | half);
       }
+    }
+    if (me == 0 && g.p2p && tid < CHIP_CAP) {
+      // replicated state: every rank steps all active particles, and accounts for the pairs of those it owns
+      const unsigned b = __ballot_sync(0xffffffffu, tid < n_act && (S.a_idx[tid] % g.world) == g.rank);
+      if (lane == 0 && b) atomicAdd(&S.acct_own, __popc(b));
     }
     PROF(2)
     // ---- 4: an owner collects the rows of its slots (polling the words themselves), sums them in CTA order, corrects
@@ -523,6 +563,34 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
       }
     }
     PROF(3)
+    // ---- 4b: while the owners correct and publish, predict the chunk to the LIKELY next block time: the smallest of the
+    //          other chunks' minima and of t + dt of this step's active particles with their timesteps unchanged (they came
+    //          with the records).  Right unless a timestep of the front runners changes; the next step checks ----------
+    if (warp == 0) {
+      unsigned long long g_min = INF_BITS;
+      for (int e = lane; e < nc; e += 32) {
+        const unsigned long long v = S.cmin[e];
+        if (v != tnb) g_min = v < g_min ? v : g_min;
+      }
+      for (int q = lane; q < n_act; q += 32) {
+        const unsigned long long v = dbits(tn + bitsd((unsigned long long)S.a_dte[q] << 52));
+        g_min = v < g_min ? v : g_min;
+      }
+      g_min = warp_min_u64_redux(g_min);
+      if (lane == 0) S.wmin[0] = g_min;
+    }
+    __syncthreads();
+    {
+      const unsigned long long gb = S.wmin[0];
+      const double tg = bitsd(gb);
+      for (int k = tid; k < cnt; k += CHIP_T) {
+        double4 pp, pv;
+        predict_to(tg, tt[k], pos[k], vel[k], acc[k], jrk[k], pp, pv);
+        ppos[k] = pp;
+        pvel[k] = pv;
+      }
+      if (tid == 0) S.pred_bits = gb;
+    }
     // ---- 5: everybody waits for the owners' headers (the other chunks' minima cannot have changed) ---------------
     alive = chip_poll(g.hdr, [&]() {
       bool ok = true;
@@ -546,31 +614,27 @@ __global__ void __launch_bounds__(CHIP_T, 1) k_chip(const GravDev g, const int p
     });
     PROF(4)
     seq += 1u;
-    n_steps += 1;
-    if (me == 0 && tid == 0) {
-      int own = n_act;
-      if (g.p2p) {  // replicated state: every rank steps all active particles, and accounts for the pairs of those it owns
-        own = 0;
-        for (int q = 0; q < n_act; q++) own += (S.a_idx[q] % g.world) == g.rank;
-      }
-      n_pairs += (long long)own * (long long)g.n_tot;
-      int b = 0;
-      while ((1 << (b + 1)) <= n_act && b < 8) b++;
-      hist[b] += 1;
+    if (me == 0 && tid == ACCT_TID) {  // (the ballots above are separated from here by the barriers of the polls)
+      n_steps += 1;
+      n_pairs += (long long)(g.p2p ? S.acct_own : n_act) * (long long)g.n_tot;
+      S.acct_own = 0;
+      S.hist[31 - __clz(n_act)] += 1;  // n_act <= CHIP_CAP = 2^8
     }
   }
 #undef PROF
+  if (me == 0 && tid == ACCT_TID) {
+    g.hdr->n_steps += n_steps;
+    g.hdr->n_pairs += n_pairs;
+    g.hdr->n_chip += n_steps;
+    for (int b = 0; b < 9; b++) g.hdr->nact_hist[b] += S.hist[b];
+  }
   if (me == 0 && tid == 0) {
     if (alive) ctl->t_next_bits = tnb;  // the block time of the step that is still to be taken (or beyond the span)
     g.hdr->chip_seq = seq;
     g.hdr->bar_counter = 0u;  // chained: the loop kernel that follows counts its grid barriers from zero
     if (pull) g.hdr->dist_prev_exch = 0;  // every CTA has read the flag: none leaves before all have published
-    g.hdr->n_steps += n_steps;
-    g.hdr->n_pairs += n_pairs;
-    g.hdr->n_chip += n_steps;
     g.hdr->fuse_ns[4] += 1;  // diagnostic: launches that got past the span check
     for (int k = 0; k < 6; k++) g.hdr->loop_cycles[k] += prof[k];
-    for (int b = 0; b < 9; b++) g.hdr->nact_hist[b] += hist[b];
   }
 }
 
