@@ -1001,6 +1001,10 @@ static int evolve_run(al26_ctx *c, const int64_t l0, int64_t *n_block_steps, int
       if (c->h_hdr->done) break;
     }
   } else {
+    if (c->chip_on) {  // the engine's error flag lives in the header: clear what an earlier call may have left
+      k_loop_prepare<<<1, 32, 0, c->stream>>>(c->g.hdr);
+      c->launches++;
+    }
     int launches_needed = 0;
     int batch = c->expected_graph_launches > 1 ? c->expected_graph_launches - 1 : 1;
     while (true) {
@@ -1011,6 +1015,8 @@ static int evolve_run(al26_ctx *c, const int64_t l0, int64_t *n_block_steps, int
       }
       batch = 1;
       if ((rc = read_header(c))) return rc;
+      if (c->chip_on && c->h_hdr->loop_error)
+        return fail(c, AL26_ECUDA, "chip engine: spin limit hit (code %d)", c->h_hdr->loop_error);
       if (c->h_hdr->done) break;
     }
     c->expected_graph_launches = launches_needed;
